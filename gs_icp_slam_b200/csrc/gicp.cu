@@ -1,0 +1,1044 @@
+// gicp.cu — Generalized-ICP tracker on the GPU behind the pygicp.FastGICP interface.
+//
+// Replaces fast_gicp::FastGICP<PointXYZ,PointXYZ> + LsqRegistration (CPU, OpenMP, PCL kd-tree):
+//   FG = submodules/fast_gicp ; fgi = FG/include/fast_gicp/gicp/impl/fast_gicp_impl.hpp ;
+//   lsq = FG/include/fast_gicp/gicp/impl/lsq_registration_impl.hpp
+//
+//   covariance_kernel   fgi:382-479 / 588-706 / 710-825  k-NN (exact, grid) -> mean -> cov/k -> Jacobi SVD
+//                       -> quaternion(U), sqrt(sigma) -> NORMALIZED_ELLIPSE covariance (+ filter compaction)
+//   cov_from_qs_kernel  fgi:828-902  covariances from (quaternion, scale) incl. the (w,x,y,z) ctor quirk
+//   linearize_kernel    fgi:242-293 + 296-352 fused: fp32 transform -> exact 1-NN -> Mahalanobis
+//                       (RCR^-1) -> e, J=[skew(Tp) | -I] -> 28-double block reduction (21 H + 6 b + err),
+//                       deterministic last-block finalisation
+//   error_kernel        fgi:355-378  sum e^T M e with frozen correspondences
+//   align()             pcl::Registration::align + fgi:225-240 + lsq:53-173 (LM loop, 6x6 LDLT on the host)
+//
+// Data layout in HBM: points fp32 xyz (12 B) + the same points in grid-cell order as
+// float4 {x,y,z,index}; covariances as the 6 unique fp64 entries (48 B, the reference stores 128-B
+// Matrix4d); Mahalanobis matrices 48 B per source point.  Compiled with -fmad=false (see gicp_math.cuh).
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include "gicp_math.cuh"
+#include "grid.cuh"
+
+namespace gsicp {
+
+constexpr int kRed = 28;       // 21 (upper triangle of H, row-major) + 6 (b) + 1 (error)
+constexpr int kLinBlock = 128;
+
+struct PoseD {  // pose in both precisions, passed by value
+  double R[3][3], t[3];
+  float Rf[3][3], tf[3];
+};
+
+// ------------------------------------------------------------------------------------------------
+// covariance kernel
+// ------------------------------------------------------------------------------------------------
+struct CovArgs {
+  int n;             // points in the cloud
+  int k;             // neighbours requested
+  float knn_max;     // compared with SQUARED distances (reference quirk, fgi:620)
+  int clamp;         // 1: values = max(values, 1e-3)  (fgi:468-469: calculate_covariances only)
+  const int32_t* filter;  // NULL: every point keeps its covariance at its own index
+  const float* xyz;
+  float* rots;       // [4n] x,y,z,w
+  float* scales;     // [3n]
+  double* cov;       // [6 * slots]
+  float* new_xyz;    // [3 * num_trackable] (only with filter)
+};
+
+template <int K>
+__global__ void __launch_bounds__(128)
+covariance_kernel(GridView g, CovArgs a) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.n) return;
+  const float qx = a.xyz[3 * (size_t)i], qy = a.xyz[3 * (size_t)i + 1], qz = a.xyz[3 * (size_t)i + 2];
+  TopK<K> nn;
+  const int kk = min(a.k, K);
+  grid_knn<K>(g, qx, qy, qz, kk, 0xffffffffu, nn);  // the query point itself is its own nearest neighbour
+
+  const int found = min(kk, a.n);
+  int reliable = 0;  // neighbours are sorted ascending, so the reliable ones are a prefix
+  for (int j = 0; j < K; j++)
+    if (j < found && nn.d2[j] < a.knn_max) reliable++;
+
+  double mean[3] = {0, 0, 0};
+  for (int j = 0; j < K; j++) {
+    if (j < reliable) {
+      const uint32_t id = nn.id[j];
+      mean[0] += (double)a.xyz[3 * (size_t)id];
+      mean[1] += (double)a.xyz[3 * (size_t)id + 1];
+      mean[2] += (double)a.xyz[3 * (size_t)id + 2];
+    }
+  }
+  const double inv_n = (double)reliable;
+  mean[0] /= inv_n; mean[1] /= inv_n; mean[2] /= inv_n;  // NaN when no neighbour is reliable, like the reference
+  double C[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+  for (int j = 0; j < K; j++) {
+    if (j < reliable) {
+      const uint32_t id = nn.id[j];
+      const double dx = (double)a.xyz[3 * (size_t)id] - mean[0];
+      const double dy = (double)a.xyz[3 * (size_t)id + 1] - mean[1];
+      const double dz = (double)a.xyz[3 * (size_t)id + 2] - mean[2];
+      C[0][0] += dx * dx; C[0][1] += dx * dy; C[0][2] += dx * dz;
+      C[1][1] += dy * dy; C[1][2] += dy * dz; C[2][2] += dz * dz;
+    }
+  }
+  const double kd = (double)a.k;  // divides by k, not by the neighbour count (fgi:635)
+  C[0][0] /= kd; C[0][1] /= kd; C[0][2] /= kd; C[1][1] /= kd; C[1][2] /= kd; C[2][2] /= kd;
+  C[1][0] = C[0][1]; C[2][0] = C[0][2]; C[2][1] = C[1][2];
+
+  double U[3][3], S[3], V[3][3];
+  svd3_jacobi(C, U, S, V);
+  double q[4];
+  quat_from_matrix(U, q);
+  a.rots[4 * (size_t)i + 0] = (float)q[0];
+  a.rots[4 * (size_t)i + 1] = (float)q[1];
+  a.rots[4 * (size_t)i + 2] = (float)q[2];
+  a.rots[4 * (size_t)i + 3] = (float)q[3];
+  a.scales[3 * (size_t)i + 0] = (float)sqrt(S[0]);
+  a.scales[3 * (size_t)i + 1] = (float)sqrt(S[1]);
+  a.scales[3 * (size_t)i + 2] = (float)sqrt(S[2]);
+
+  int slot = i;
+  if (a.filter) {
+    const int f = a.filter[i];
+    if (f == 0) return;
+    slot = f - 1;
+  }
+  double values[3];
+  if (S[1] == 0.0) {  // NORMALIZED_ELLIPSE (fgi:460-469, 681-689): normalised by the MIDDLE singular value
+    values[0] = values[1] = values[2] = 1e-9;
+  } else {
+    values[0] = S[0] / S[1]; values[1] = S[1] / S[1]; values[2] = S[2] / S[1];
+    if (a.clamp) {
+      values[0] = fmax(values[0], 1e-3); values[1] = fmax(values[1], 1e-3); values[2] = fmax(values[2], 1e-3);
+    }
+  }
+  double Rg[3][3];
+  a_diag_bt(U, values, V, Rg);
+  double* o = a.cov + 6 * (size_t)slot;
+  // the reference keeps the full (numerically almost symmetric) 3x3; we keep its symmetric part's
+  // upper triangle taken from the upper entries
+  o[0] = Rg[0][0]; o[1] = Rg[0][1]; o[2] = Rg[0][2]; o[3] = Rg[1][1]; o[4] = Rg[1][2]; o[5] = Rg[2][2];
+  if (a.filter) {
+    a.new_xyz[3 * (size_t)slot + 0] = qx;
+    a.new_xyz[3 * (size_t)slot + 1] = qy;
+    a.new_xyz[3 * (size_t)slot + 2] = qz;
+  }
+}
+
+// covariances from (quaternion, scale) (fgi:828-902)
+__global__ void cov_from_qs_kernel(int n, const float* __restrict__ rots, const float* __restrict__ scales,
+                                   double* __restrict__ cov) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double sv[3];
+  for (int d = 0; d < 3; d++) {
+    const double s = (double)scales[3 * (size_t)i + d];
+    sv[d] = s * s;
+  }
+  if (sv[1] < 1e-3) {
+    sv[0] = sv[1] = sv[2] = 1e-3;
+  } else {
+    const double m = sv[1];
+    sv[0] = sv[0] / m; sv[1] = sv[1] / m; sv[2] = sv[2] / m;
+  }
+  // Reference quirk (fgi:890-894): the stored (x,y,z,w) is passed to a (w,x,y,z) constructor.
+  double w = (double)rots[4 * (size_t)i + 0], x = (double)rots[4 * (size_t)i + 1];
+  double y = (double)rots[4 * (size_t)i + 2], z = (double)rots[4 * (size_t)i + 3];
+  const double nrm = sqrt(x * x + y * y + z * z + w * w);
+  if (nrm > 0.0) {  // Eigen's normalized() leaves a zero quaternion untouched
+    x /= nrm; y /= nrm; z /= nrm; w /= nrm;
+  }
+  double R[3][3], C[3][3];
+  quat_to_matrix(x, y, z, w, R);
+  a_diag_bt(R, sv, R, C);
+  double* o = cov + 6 * (size_t)i;
+  o[0] = C[0][0]; o[1] = C[0][1]; o[2] = C[0][2]; o[3] = C[1][1]; o[4] = C[1][2]; o[5] = C[2][2];
+}
+
+// ------------------------------------------------------------------------------------------------
+// linearize / error kernels
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// block-level reduction of NV doubles per thread into partial[blockIdx][NV]; the last block to finish
+// sums the partials in block order (deterministic) into out[NV].
+template <int NV>
+__device__ __forceinline__ void block_reduce_finalize(double* v, double* __restrict__ partial, double* __restrict__ out,
+                                                      unsigned int* __restrict__ counter) {
+  __shared__ double s_red[kLinBlock / 32][NV];
+  __shared__ bool s_last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < NV; k++) {
+    const double r = warp_sum_d(v[k]);
+    if (lane == 0) s_red[warp][k] = r;
+  }
+  __syncthreads();
+  if (threadIdx.x < NV) {
+    double r = 0.0;
+#pragma unroll
+    for (int w = 0; w < kLinBlock / 32; w++) r += s_red[w][threadIdx.x];
+    partial[(size_t)blockIdx.x * NV + threadIdx.x] = r;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int done = atomicAdd(counter, 1u);
+    s_last = (done == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    if (threadIdx.x < NV) {
+      double r = 0.0;
+      for (unsigned int b = 0; b < gridDim.x; b++) r += partial[(size_t)b * NV + threadIdx.x];
+      out[threadIdx.x] = r;
+    }
+    if (threadIdx.x == 0) *counter = 0u;  // ready for the next launch
+  }
+}
+
+struct LinArgs {
+  int begin, end;          // source range of this rank
+  double max_corr_sq;      // corr_dist_threshold_^2 in double (fgi:271)
+  const float* src_xyz;
+  const double* src_cov;
+  const float* tgt_xyz;
+  const double* tgt_cov;
+  int32_t* corr;
+  float* sqd;
+  double* mahal;           // [6 * n_src]
+  double* partial;
+  double* out;             // [28]
+  unsigned int* counter;
+};
+
+__global__ void __launch_bounds__(kLinBlock)
+linearize_kernel(GridView tgt, PoseD T, LinArgs a) {
+  const int i = a.begin + blockIdx.x * blockDim.x + threadIdx.x;
+  double v[kRed];
+#pragma unroll
+  for (int k = 0; k < kRed; k++) v[k] = 0.0;
+
+  if (i < a.end) {
+    const float px = a.src_xyz[3 * (size_t)i], py = a.src_xyz[3 * (size_t)i + 1], pz = a.src_xyz[3 * (size_t)i + 2];
+    // fp32 transform of the query (fgi:260-262): ((r0*x + r1*y) + r2*z) + t
+    const float tx = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(T.Rf[0][0], px), __fmul_rn(T.Rf[0][1], py)), __fmul_rn(T.Rf[0][2], pz)), T.tf[0]);
+    const float ty = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(T.Rf[1][0], px), __fmul_rn(T.Rf[1][1], py)), __fmul_rn(T.Rf[1][2], pz)), T.tf[1]);
+    const float tz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(T.Rf[2][0], px), __fmul_rn(T.Rf[2][1], py)), __fmul_rn(T.Rf[2][2], pz)), T.tf[2]);
+    TopK<1> nn;
+    grid_knn<1>(tgt, tx, ty, tz, 1, 0xffffffffu, nn);
+    const float d2 = nn.d2[0];
+    a.sqd[i] = d2;
+    const bool matched = (tgt.n > 0) && ((double)d2 < a.max_corr_sq);
+    const int32_t j = matched ? (int32_t)nn.id[0] : -1;
+    a.corr[i] = j;
+    if (matched) {
+      const double* ca = a.src_cov + 6 * (size_t)i;
+      const double* cb = a.tgt_cov + 6 * (size_t)j;
+      const double A[3][3] = {{ca[0], ca[1], ca[2]}, {ca[1], ca[3], ca[4]}, {ca[2], ca[4], ca[5]}};
+      // RCR = C_B + R C_A R^T  (fgi:280)
+      double RA[3][3], RCR[3][3];
+#pragma unroll
+      for (int r = 0; r < 3; r++)
+#pragma unroll
+        for (int c = 0; c < 3; c++) RA[r][c] = (T.R[r][0] * A[0][c] + T.R[r][1] * A[1][c]) + T.R[r][2] * A[2][c];
+      const double B[3][3] = {{cb[0], cb[1], cb[2]}, {cb[1], cb[3], cb[4]}, {cb[2], cb[4], cb[5]}};
+#pragma unroll
+      for (int r = 0; r < 3; r++)
+#pragma unroll
+        for (int c = 0; c < 3; c++) RCR[r][c] = B[r][c] + ((RA[r][0] * T.R[c][0] + RA[r][1] * T.R[c][1]) + RA[r][2] * T.R[c][2]);
+      double M[3][3];
+      if (!inverse3(RCR, M)) {
+        // reference: pseudo-inverse via complete orthogonal decomposition (fgi:283-286); a singular
+        // RCR cannot occur with regularised covariances — contribute nothing.
+#pragma unroll
+        for (int r = 0; r < 3; r++)
+#pragma unroll
+          for (int c = 0; c < 3; c++) M[r][c] = 0.0;
+      }
+      double* mo = a.mahal + 6 * (size_t)i;
+      mo[0] = M[0][0]; mo[1] = M[0][1]; mo[2] = M[0][2]; mo[3] = M[1][1]; mo[4] = M[1][2]; mo[5] = M[2][2];
+      // use the stored (symmetric) representation from here on so linearize and compute_error agree
+      M[1][0] = M[0][1]; M[2][0] = M[0][2]; M[2][1] = M[1][2];
+
+      const double ax = (double)px, ay = (double)py, az = (double)pz;
+      const double qx = ((T.R[0][0] * ax + T.R[0][1] * ay) + T.R[0][2] * az) + T.t[0];
+      const double qy = ((T.R[1][0] * ax + T.R[1][1] * ay) + T.R[1][2] * az) + T.t[1];
+      const double qz = ((T.R[2][0] * ax + T.R[2][1] * ay) + T.R[2][2] * az) + T.t[2];
+      const double e[3] = {(double)a.tgt_xyz[3 * (size_t)j] - qx, (double)a.tgt_xyz[3 * (size_t)j + 1] - qy,
+                           (double)a.tgt_xyz[3 * (size_t)j + 2] - qz};
+      double Me[3];
+#pragma unroll
+      for (int r = 0; r < 3; r++) Me[r] = (M[r][0] * e[0] + M[r][1] * e[1]) + M[r][2] * e[2];
+      v[27] = (e[0] * Me[0] + e[1] * Me[1]) + e[2] * Me[2];
+
+      // J = [S | -I], S = skew(q):  S = [[0,-qz,qy],[qz,0,-qx],[-qy,qx,0]]
+      const double S[3][3] = {{0.0, -qz, qy}, {qz, 0.0, -qx}, {-qy, qx, 0.0}};
+      double MS[3][3];  // M * S
+#pragma unroll
+      for (int r = 0; r < 3; r++)
+#pragma unroll
+        for (int c = 0; c < 3; c++) MS[r][c] = (M[r][0] * S[0][c] + M[r][1] * S[1][c]) + M[r][2] * S[2][c];
+      double H[6][6];
+#pragma unroll
+      for (int r = 0; r < 3; r++)
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+          H[r][c] = (S[0][r] * MS[0][c] + S[1][r] * MS[1][c]) + S[2][r] * MS[2][c];  // S^T M S
+          H[r][3 + c] = -((S[0][r] * M[0][c] + S[1][r] * M[1][c]) + S[2][r] * M[2][c]);  // -S^T M
+          H[3 + r][3 + c] = M[r][c];
+        }
+      int o = 0;
+#pragma unroll
+      for (int r = 0; r < 6; r++)
+#pragma unroll
+        for (int c = r; c < 6; c++) v[o++] = H[r][c];
+#pragma unroll
+      for (int r = 0; r < 3; r++) {
+        v[21 + r] = (S[0][r] * Me[0] + S[1][r] * Me[1]) + S[2][r] * Me[2];  // S^T M e
+        v[24 + r] = -Me[r];
+      }
+    }
+  }
+  block_reduce_finalize<kRed>(v, a.partial, a.out, a.counter);
+}
+
+struct ErrArgs {
+  int begin, end;
+  const float* src_xyz;
+  const float* tgt_xyz;
+  const int32_t* corr;
+  const double* mahal;
+  double* partial;
+  double* out;  // [1]
+  unsigned int* counter;
+};
+
+__global__ void __launch_bounds__(kLinBlock)
+error_kernel(PoseD T, ErrArgs a) {
+  const int i = a.begin + blockIdx.x * blockDim.x + threadIdx.x;
+  double v[1] = {0.0};
+  if (i < a.end) {
+    const int32_t j = a.corr[i];
+    if (j >= 0) {
+      const double ax = (double)a.src_xyz[3 * (size_t)i], ay = (double)a.src_xyz[3 * (size_t)i + 1],
+                   az = (double)a.src_xyz[3 * (size_t)i + 2];
+      const double qx = ((T.R[0][0] * ax + T.R[0][1] * ay) + T.R[0][2] * az) + T.t[0];
+      const double qy = ((T.R[1][0] * ax + T.R[1][1] * ay) + T.R[1][2] * az) + T.t[1];
+      const double qz = ((T.R[2][0] * ax + T.R[2][1] * ay) + T.R[2][2] * az) + T.t[2];
+      const double e[3] = {(double)a.tgt_xyz[3 * (size_t)j] - qx, (double)a.tgt_xyz[3 * (size_t)j + 1] - qy,
+                           (double)a.tgt_xyz[3 * (size_t)j + 2] - qz};
+      const double* m = a.mahal + 6 * (size_t)i;
+      const double Me0 = (m[0] * e[0] + m[1] * e[1]) + m[2] * e[2];
+      const double Me1 = (m[1] * e[0] + m[3] * e[1]) + m[4] * e[2];
+      const double Me2 = (m[2] * e[0] + m[4] * e[1]) + m[5] * e[2];
+      v[0] = (e[0] * Me0 + e[1] * Me1) + e[2] * Me2;
+    }
+  }
+  block_reduce_finalize<1>(v, a.partial, a.out, a.counter);
+}
+
+__global__ void f64_to_f32_kernel(size_t n, const double* __restrict__ in, float* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (float)in[i];
+}
+
+__global__ void identity_filter_kernel(int n, int32_t* f) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) f[i] = i + 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side: 6x6 LDLT, SE(3) helpers
+// ------------------------------------------------------------------------------------------------
+// Pivoted LDL^T of a symmetric 6x6 and solve, following Eigen's LDLT (Eigen/src/Cholesky/LDLT.h:
+// unblocked lower factorisation with diagonal pivoting, then P^T L^-T D^-1 L^-1 P b).
+static void ldlt_solve6(const double Hin[6][6], const double rhs[6], double x[6]) {
+  const int n = 6;
+  double A[6][6];
+  int tr[6];
+  for (int i = 0; i < n; i++)
+    for (int j = 0; j < n; j++) A[i][j] = Hin[i][j];
+  for (int k = 0; k < n; k++) {
+    int piv = k;
+    double big = std::fabs(A[k][k]);
+    for (int i = k + 1; i < n; i++)
+      if (std::fabs(A[i][i]) > big) {
+        big = std::fabs(A[i][i]);
+        piv = i;
+      }
+    tr[k] = piv;
+    if (piv != k) {  // symmetric row/column interchange on the lower triangle
+      const int s = n - piv - 1;
+      for (int c = 0; c < k; c++) std::swap(A[k][c], A[piv][c]);
+      for (int r = 0; r < s; r++) std::swap(A[piv + 1 + r][k], A[piv + 1 + r][piv]);
+      std::swap(A[k][k], A[piv][piv]);
+      for (int i = k + 1; i < piv; i++) std::swap(A[i][k], A[piv][i]);
+    }
+    const int rs = n - k - 1;
+    if (k > 0) {
+      double temp[6];
+      for (int c = 0; c < k; c++) temp[c] = A[c][c] * A[k][c];
+      double acc = 0.0;
+      for (int c = 0; c < k; c++) acc += A[k][c] * temp[c];
+      A[k][k] -= acc;
+      for (int r = 0; r < rs; r++) {
+        double a2 = 0.0;
+        for (int c = 0; c < k; c++) a2 += A[k + 1 + r][c] * temp[c];
+        A[k + 1 + r][k] -= a2;
+      }
+    }
+    const double akk = A[k][k];
+    const bool valid = std::fabs(akk) > 0.0;
+    if (k == 0 && !valid) {
+      for (int j = 0; j < n; j++) tr[j] = j;
+      break;
+    }
+    if (rs > 0 && valid)
+      for (int r = 0; r < rs; r++) A[k + 1 + r][k] /= akk;
+  }
+  double y[6];
+  for (int i = 0; i < n; i++) y[i] = rhs[i];
+  for (int k = 0; k < n; k++) std::swap(y[k], y[tr[k]]);          // P b
+  for (int i = 0; i < n; i++)                                      // L^-1
+    for (int c = 0; c < i; c++) y[i] -= A[i][c] * y[c];
+  const double tol = 1.0 / std::numeric_limits<double>::max();
+  for (int i = 0; i < n; i++) y[i] = (std::fabs(A[i][i]) > tol) ? y[i] / A[i][i] : 0.0;  // D^-1
+  for (int i = n - 1; i >= 0; i--)                                 // L^-T
+    for (int c = i + 1; c < n; c++) y[i] -= A[c][i] * y[c];
+  for (int k = n - 1; k >= 0; k--) std::swap(y[k], y[tr[k]]);      // P^T
+  for (int i = 0; i < n; i++) x[i] = y[i];
+}
+
+struct Iso {  // rigid transform, double
+  double R[3][3], t[3];
+};
+
+static void so3_exp_matrix(const double w[3], double R[3][3]) {  // FG/include/fast_gicp/so3/so3.hpp:58-77
+  const double theta_sq = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
+  double imag, real;
+  if (theta_sq < 1e-10) {
+    const double theta_quad = theta_sq * theta_sq;
+    imag = 0.5 - 1.0 / 48.0 * theta_sq + 1.0 / 3840.0 * theta_quad;
+    real = 1.0 - 1.0 / 8.0 * theta_sq + 1.0 / 384.0 * theta_quad;
+  } else {
+    const double theta = std::sqrt(theta_sq);
+    const double half = 0.5 * theta;
+    imag = std::sin(half) / theta;
+    real = std::cos(half);
+  }
+  quat_to_matrix(imag * w[0], imag * w[1], imag * w[2], real, R);
+}
+
+static Iso iso_mul(const Iso& a, const Iso& b) {  // a * b
+  Iso r;
+  for (int i = 0; i < 3; i++) {
+    for (int j = 0; j < 3; j++) r.R[i][j] = (a.R[i][0] * b.R[0][j] + a.R[i][1] * b.R[1][j]) + a.R[i][2] * b.R[2][j];
+    r.t[i] = ((a.R[i][0] * b.t[0] + a.R[i][1] * b.t[1]) + a.R[i][2] * b.t[2]) + a.t[i];
+  }
+  return r;
+}
+
+static PoseD make_pose(const Iso& x) {
+  PoseD p;
+  for (int i = 0; i < 3; i++) {
+    for (int j = 0; j < 3; j++) {
+      p.R[i][j] = x.R[i][j];
+      p.Rf[i][j] = (float)x.R[i][j];
+    }
+    p.t[i] = x.t[i];
+    p.tf[i] = (float)x.t[i];
+  }
+  return p;
+}
+
+struct Cloud {
+  int n = 0;           // points currently held (after a *_with_filter call: the trackable subset)
+  Scratch xyz;         // float [3n]
+  Scratch xyz_alt;     // compaction target
+  DeviceGrid grid;
+  Scratch cov;         // double [6 * cov_n]
+  int cov_n = 0;
+  Scratch rots, scales;
+  int rots_n = 0, scales_n = 0;  // element counts (4 * N_all, 3 * N_all)
+  Scratch filter;      // int32 [filter_n]
+  int filter_n = -1, num_trackable = 0;
+  void clear_cov() { cov_n = 0; rots_n = 0; scales_n = 0; }
+};
+
+}  // namespace gsicp
+
+using namespace gsicp;
+
+struct gsicp_gicp {
+  Cloud src, tgt;
+  double max_corr = (double)std::numeric_limits<float>::max();  // corr_dist_threshold_ (fgi:18)
+  float knn_max = 0.5f;
+  int k = 10;
+  int max_iterations = 64;
+  double rot_eps = 2e-3, trans_eps = 5e-4;
+  int lm_max_iterations = 10;
+  double lm_init_lambda_factor = 1e-9, lm_lambda = -1.0;
+  bool converged = false;
+  int nr_iterations = 0;
+  float final_transformation[16];
+  double final_hessian[36];
+  cudaStream_t stream = 0;
+  Scratch corr, sqd, mahal, partial, red_out, counter, staging_dev;
+  int corr_n = 0;
+  double* h_red = nullptr;     // pinned [28]
+  void* h_stage = nullptr;     // pinned staging for H2D conversions
+  size_t h_stage_cap = 0;
+  int shard_count = 1, shard_index = 0;
+  gsicp_allreduce_fn reduce = nullptr;
+  void* reduce_user = nullptr;
+  bool timing = false;
+  double t_cov = 0, t_lin = 0, t_err = 0;
+  int n_lin = 0, n_err = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+namespace {
+
+int ensure_stage(gsicp_gicp* h, size_t bytes) {
+  if (bytes <= h->h_stage_cap) return GSICP_OK;
+  if (h->h_stage) cudaFreeHost(h->h_stage);
+  h->h_stage = nullptr;
+  h->h_stage_cap = 0;
+  const size_t want = bytes + bytes / 2 + 4096;
+  GSICP_CUDA(cudaMallocHost(&h->h_stage, want));
+  h->h_stage_cap = want;
+  return GSICP_OK;
+}
+
+struct StageTimer {  // accumulates device time of a stage when timing is enabled
+  gsicp_gicp* h;
+  double* acc;
+  StageTimer(gsicp_gicp* hh, double* a) : h(hh), acc(a) {
+    if (h->timing) cudaEventRecord(h->ev0, h->stream);
+  }
+  void stop() {
+    if (h->timing) {
+      cudaEventRecord(h->ev1, h->stream);
+      cudaEventSynchronize(h->ev1);
+      float ms = 0;
+      cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+      *acc += ms;
+    }
+  }
+};
+
+int set_cloud(gsicp_gicp* h, Cloud& c, const void* xyz, int n, int is_f32, bool device_src) {
+  if (n < 0 || (n > 0 && !xyz)) {
+    set_error("set_input: bad arguments");
+    return GSICP_EINVAL;
+  }
+  c.n = n;
+  c.clear_cov();
+  if (n == 0) return GSICP_OK;
+  if (int e = c.xyz.ensure((size_t)n * 3 * sizeof(float))) return e;
+  const size_t cnt = (size_t)n * 3;
+  if (device_src) {
+    GSICP_CUDA(cudaMemcpyAsync(c.xyz.ptr, xyz, cnt * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
+  } else if (is_f32) {
+    if (int e = ensure_stage(h, cnt * sizeof(float))) return e;
+    GSICP_CUDA(cudaStreamSynchronize(h->stream));  // staging buffer reuse
+    std::memcpy(h->h_stage, xyz, cnt * sizeof(float));
+    GSICP_CUDA(cudaMemcpyAsync(c.xyz.ptr, h->h_stage, cnt * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  } else {
+    // float64 from numpy (main.cpp:37-45 eigen2pcl casts to float): convert while staging
+    if (int e = ensure_stage(h, cnt * sizeof(float))) return e;
+    GSICP_CUDA(cudaStreamSynchronize(h->stream));
+    const double* in = (const double*)xyz;
+    float* out = (float*)h->h_stage;
+    for (size_t i = 0; i < cnt; i++) out[i] = (float)in[i];
+    GSICP_CUDA(cudaMemcpyAsync(c.xyz.ptr, h->h_stage, cnt * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  }
+  return c.grid.build(c.xyz.as<float>(), n, h->stream);
+}
+
+int set_filter(gsicp_gicp* h, Cloud& c, int num_trackable, const int32_t* filter, int n) {
+  if (n < 0 || num_trackable < 0 || (n > 0 && !filter)) {
+    set_error("set_filter: bad arguments");
+    return GSICP_EINVAL;
+  }
+  c.num_trackable = num_trackable;
+  c.filter_n = n;
+  if (n == 0) return GSICP_OK;
+  if (int e = c.filter.ensure((size_t)n * 4)) return e;
+  if (int e = ensure_stage(h, (size_t)n * 4)) return e;
+  GSICP_CUDA(cudaStreamSynchronize(h->stream));
+  std::memcpy(h->h_stage, filter, (size_t)n * 4);
+  GSICP_CUDA(cudaMemcpyAsync(c.filter.ptr, h->h_stage, (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
+  return GSICP_OK;
+}
+
+// covariances of a cloud; with_filter: keep only trackable points afterwards (fgi:588-706 / 710-825)
+int compute_covariances(gsicp_gicp* h, Cloud& c, bool with_filter, bool clamp) {
+  const int n = c.n;
+  if (n == 0) {
+    fprintf(stderr, "no point cloud\n");
+    return GSICP_OK;
+  }
+  if (h->k > 32 || h->k < 1) {
+    set_error("correspondence randomness k=%d unsupported (1..32)", h->k);
+    return GSICP_EINVAL;
+  }
+  int slots = n;
+  const int32_t* d_filter = nullptr;
+  if (with_filter) {
+    if (c.filter_n < 0) {  // no filter ever set: every point is trackable (the reference would read out of bounds)
+      if (int e = c.filter.ensure((size_t)n * 4)) return e;
+      GSICP_LAUNCH(identity_filter_kernel, (n + 255) / 256, 256, 0, h->stream, n, c.filter.as<int32_t>());
+      c.num_trackable = n;
+    } else if (c.filter_n != n) {
+      set_error("filter length %d does not match the cloud size %d", c.filter_n, n);
+      return GSICP_ESTATE;
+    }
+    slots = c.num_trackable;
+    d_filter = c.filter.as<int32_t>();
+  }
+  if (int e = c.cov.ensure((size_t)(slots > 0 ? slots : 1) * 6 * sizeof(double))) return e;
+  if (int e = c.rots.ensure((size_t)n * 4 * sizeof(float))) return e;
+  if (int e = c.scales.ensure((size_t)n * 3 * sizeof(float))) return e;
+  if (with_filter)
+    if (int e = c.xyz_alt.ensure((size_t)(slots > 0 ? slots : 1) * 3 * sizeof(float))) return e;
+  CovArgs a;
+  a.n = n; a.k = h->k; a.knn_max = h->knn_max; a.clamp = clamp ? 1 : 0;
+  a.filter = d_filter; a.xyz = c.xyz.as<float>(); a.rots = c.rots.as<float>(); a.scales = c.scales.as<float>();
+  a.cov = c.cov.as<double>(); a.new_xyz = with_filter ? c.xyz_alt.as<float>() : nullptr;
+  const int grid = (n + 127) / 128;
+  if (h->k <= 10) GSICP_LAUNCH(covariance_kernel<10>, grid, 128, 0, h->stream, c.grid.view(), a);
+  else if (h->k <= 20) GSICP_LAUNCH(covariance_kernel<20>, grid, 128, 0, h->stream, c.grid.view(), a);
+  else GSICP_LAUNCH(covariance_kernel<32>, grid, 128, 0, h->stream, c.grid.view(), a);
+  GSICP_CUDA(cudaGetLastError());
+  c.rots_n = 4 * n;
+  c.scales_n = 3 * n;
+  c.cov_n = slots;
+  if (with_filter) {
+    std::swap(c.xyz, c.xyz_alt);
+    c.n = slots;
+    c.filter_n = -1;  // consumed; a new cloud needs a new filter
+    if (int e = c.grid.build(c.xyz.as<float>(), c.n, h->stream)) return e;
+  }
+  return GSICP_OK;
+}
+
+int covs_from_qs(gsicp_gicp* h, Cloud& c, const float* rots, const float* scales, int n) {
+  if (n < 0 || (n > 0 && (!rots || !scales))) return GSICP_EINVAL;
+  if (int e = c.cov.ensure((size_t)(n > 0 ? n : 1) * 6 * sizeof(double))) return e;
+  if (int e = c.rots.ensure((size_t)(n > 0 ? n : 1) * 4 * sizeof(float))) return e;
+  if (int e = c.scales.ensure((size_t)(n > 0 ? n : 1) * 3 * sizeof(float))) return e;
+  if (n > 0) {
+    if (int e = ensure_stage(h, (size_t)n * 7 * sizeof(float))) return e;
+    GSICP_CUDA(cudaStreamSynchronize(h->stream));
+    float* st = (float*)h->h_stage;
+    std::memcpy(st, rots, (size_t)n * 4 * sizeof(float));
+    std::memcpy(st + (size_t)n * 4, scales, (size_t)n * 3 * sizeof(float));
+    GSICP_CUDA(cudaMemcpyAsync(c.rots.ptr, st, (size_t)n * 4 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    GSICP_CUDA(cudaMemcpyAsync(c.scales.ptr, st + (size_t)n * 4, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice,
+                               h->stream));
+    GSICP_LAUNCH(cov_from_qs_kernel, (n + 255) / 256, 256, 0, h->stream, n, c.rots.as<float>(), c.scales.as<float>(),
+                 c.cov.as<double>());
+    GSICP_CUDA(cudaGetLastError());
+  }
+  c.rots_n = 4 * n;
+  c.scales_n = 3 * n;
+  c.cov_n = n;
+  return GSICP_OK;
+}
+
+void shard_range(const gsicp_gicp* h, int n, int& begin, int& end) {
+  if (h->shard_count <= 1) {
+    begin = 0;
+    end = n;
+    return;
+  }
+  const long long per = ((long long)n + h->shard_count - 1) / h->shard_count;
+  begin = (int)std::min<long long>(n, per * h->shard_index);
+  end = (int)std::min<long long>(n, per * (h->shard_index + 1));
+}
+
+int ensure_lin_buffers(gsicp_gicp* h) {
+  const int n = h->src.n;
+  const int blocks = (n + kLinBlock - 1) / kLinBlock + 1;
+  if (int e = h->corr.ensure((size_t)(n + 1) * 4)) return e;
+  if (int e = h->sqd.ensure((size_t)(n + 1) * 4)) return e;
+  if (int e = h->mahal.ensure((size_t)(n + 1) * 6 * sizeof(double))) return e;
+  if (int e = h->partial.ensure((size_t)blocks * kRed * sizeof(double))) return e;
+  if (int e = h->red_out.ensure(kRed * sizeof(double))) return e;
+  if (!h->counter.ptr) {
+    if (int e = h->counter.ensure(sizeof(unsigned int))) return e;
+    GSICP_CUDA(cudaMemsetAsync(h->counter.ptr, 0, sizeof(unsigned int), h->stream));
+  }
+  if (!h->h_red) GSICP_CUDA(cudaMallocHost(&h->h_red, kRed * sizeof(double)));
+  return GSICP_OK;
+}
+
+// fgi:296-352.  H may be null (error only).
+int run_linearize(gsicp_gicp* h, const Iso& x, double H[6][6], double b[6], double* err) {
+  if (int e = ensure_lin_buffers(h)) return e;
+  if (h->corr_n != h->src.n) {
+    // sharded runs leave the other ranks' entries untouched: start from "unmatched"
+    GSICP_CUDA(cudaMemsetAsync(h->corr.ptr, 0xff, (size_t)(h->src.n + 1) * 4, h->stream));
+    GSICP_CUDA(cudaMemsetAsync(h->sqd.ptr, 0, (size_t)(h->src.n + 1) * 4, h->stream));
+    h->corr_n = h->src.n;
+  }
+  StageTimer tm(h, &h->t_lin);
+  int begin, end;
+  shard_range(h, h->src.n, begin, end);
+  LinArgs a;
+  a.begin = begin; a.end = end;
+  a.max_corr_sq = h->max_corr * h->max_corr;
+  a.src_xyz = h->src.xyz.as<float>(); a.src_cov = h->src.cov.as<double>();
+  a.tgt_xyz = h->tgt.xyz.as<float>(); a.tgt_cov = h->tgt.cov.as<double>();
+  a.corr = h->corr.as<int32_t>(); a.sqd = h->sqd.as<float>(); a.mahal = h->mahal.as<double>();
+  a.partial = h->partial.as<double>(); a.out = h->red_out.as<double>(); a.counter = h->counter.as<unsigned int>();
+  int blocks = (end - begin + kLinBlock - 1) / kLinBlock;
+  if (blocks < 1) blocks = 1;
+  GSICP_LAUNCH(linearize_kernel, blocks, kLinBlock, 0, h->stream, h->tgt.grid.view(), make_pose(x), a);
+  if (h->shard_count > 1 && h->reduce) {
+    const int rc = h->reduce(h->reduce_user, h->red_out.as<double>(), kRed, (void*)h->stream);
+    if (rc != 0) {
+      set_error("all-reduce callback failed (%d)", rc);
+      return GSICP_ECUDA;
+    }
+  }
+  GSICP_CUDA(cudaMemcpyAsync(h->h_red, h->red_out.ptr, kRed * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  tm.stop();
+  GSICP_CUDA(cudaStreamSynchronize(h->stream));
+  h->n_lin++;
+  if (H && b) {
+    int o = 0;
+    for (int r = 0; r < 6; r++)
+      for (int c = r; c < 6; c++) {
+        H[r][c] = h->h_red[o];
+        H[c][r] = h->h_red[o];
+        o++;
+      }
+    for (int r = 0; r < 6; r++) b[r] = h->h_red[21 + r];
+  }
+  *err = h->h_red[27];
+  return GSICP_OK;
+}
+
+int run_error(gsicp_gicp* h, const Iso& x, double* err) {  // fgi:355-378
+  if (int e = ensure_lin_buffers(h)) return e;
+  StageTimer tm(h, &h->t_err);
+  int begin, end;
+  shard_range(h, h->src.n, begin, end);
+  ErrArgs a;
+  a.begin = begin; a.end = end;
+  a.src_xyz = h->src.xyz.as<float>(); a.tgt_xyz = h->tgt.xyz.as<float>();
+  a.corr = h->corr.as<int32_t>(); a.mahal = h->mahal.as<double>();
+  a.partial = h->partial.as<double>(); a.out = h->red_out.as<double>(); a.counter = h->counter.as<unsigned int>();
+  int blocks = (end - begin + kLinBlock - 1) / kLinBlock;
+  if (blocks < 1) blocks = 1;
+  GSICP_LAUNCH(error_kernel, blocks, kLinBlock, 0, h->stream, make_pose(x), a);
+  if (h->shard_count > 1 && h->reduce) {
+    const int rc = h->reduce(h->reduce_user, h->red_out.as<double>(), 1, (void*)h->stream);
+    if (rc != 0) return GSICP_ECUDA;
+  }
+  GSICP_CUDA(cudaMemcpyAsync(h->h_red, h->red_out.ptr, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  tm.stop();
+  GSICP_CUDA(cudaStreamSynchronize(h->stream));
+  h->n_err++;
+  *err = h->h_red[0];
+  return GSICP_OK;
+}
+
+bool is_converged(const gsicp_gicp* h, const Iso& delta) {  // lsq:81-90
+  double m = 0.0;
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) m = std::max(m, (1.0 / h->rot_eps) * std::fabs(delta.R[i][j] - (i == j ? 1.0 : 0.0)));
+  double mt = 0.0;
+  for (int i = 0; i < 3; i++) mt = std::max(mt, (1.0 / h->trans_eps) * std::fabs(delta.t[i]));
+  return std::max(m, mt) < 1;
+}
+
+// lsq:125-173.  Returns 1 = step taken / converged, 0 = failed ("lm not converged"), <0 = error.
+int step_lm(gsicp_gicp* h, Iso& x0, Iso& delta) {
+  double H[6][6], b[6], y0;
+  if (int e = run_linearize(h, x0, H, b, &y0)) return e;
+  if (h->lm_lambda < 0.0) {
+    double mx = 0.0;
+    for (int i = 0; i < 6; i++) mx = std::max(mx, std::fabs(H[i][i]));
+    h->lm_lambda = h->lm_init_lambda_factor * mx;
+  }
+  double nu = 2.0;
+  for (int it = 0; it < h->lm_max_iterations; it++) {
+    double A[6][6], nb[6], d[6];
+    for (int i = 0; i < 6; i++) {
+      for (int j = 0; j < 6; j++) A[i][j] = H[i][j] + (i == j ? h->lm_lambda : 0.0);
+      nb[i] = -b[i];
+    }
+    ldlt_solve6(A, nb, d);
+    for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++) delta.R[i][j] = (i == j);
+    so3_exp_matrix(d, delta.R);
+    delta.t[0] = d[3]; delta.t[1] = d[4]; delta.t[2] = d[5];
+    const Iso xi = iso_mul(delta, x0);
+    double yi;
+    if (int e = run_error(h, xi, &yi)) return e;
+    double dot = 0.0;
+    for (int i = 0; i < 6; i++) dot += d[i] * (h->lm_lambda * d[i] - b[i]);
+    const double rho = (y0 - yi) / dot;
+    if (rho < 0) {
+      if (is_converged(h, delta)) return 1;
+      h->lm_lambda = nu * h->lm_lambda;
+      nu = 2 * nu;
+      continue;
+    }
+    x0 = xi;
+    h->lm_lambda = h->lm_lambda * std::max(1.0 / 3.0, 1 - std::pow(2 * rho - 1, 3));
+    for (int i = 0; i < 6; i++)
+      for (int j = 0; j < 6; j++) h->final_hessian[6 * i + j] = H[i][j];
+    return 1;
+  }
+  return 0;
+}
+
+int copy_out(gsicp_gicp* h, const Scratch& s, size_t bytes, void* out) {
+  if (bytes == 0) return GSICP_OK;
+  if (!out) return GSICP_EINVAL;
+  GSICP_CUDA(cudaMemcpyAsync(out, s.ptr, bytes, cudaMemcpyDeviceToHost, h->stream));
+  GSICP_CUDA(cudaStreamSynchronize(h->stream));
+  return GSICP_OK;
+}
+
+int copy_cov_out(gsicp_gicp* h, const Cloud& c, double* out) {
+  if (c.cov_n == 0) return GSICP_OK;
+  std::vector<double> tmp((size_t)c.cov_n * 6);
+  if (int e = copy_out(h, c.cov, tmp.size() * sizeof(double), tmp.data())) return e;
+  for (int i = 0; i < c.cov_n; i++) {
+    const double* s = &tmp[(size_t)i * 6];
+    double* o = out + (size_t)i * 9;
+    o[0] = s[0]; o[1] = s[1]; o[2] = s[2]; o[3] = s[1]; o[4] = s[3]; o[5] = s[4]; o[6] = s[2]; o[7] = s[4]; o[8] = s[5];
+  }
+  return GSICP_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+gsicp_gicp* gsicp_gicp_create(void) {
+  gsicp_gicp* h = new gsicp_gicp();
+  for (int i = 0; i < 16; i++) h->final_transformation[i] = (i % 5 == 0) ? 1.f : 0.f;
+  for (int i = 0; i < 36; i++) h->final_hessian[i] = (i % 7 == 0) ? 1.0 : 0.0;
+  const char* t = std::getenv("GSICP_TIMING");
+  h->timing = t && t[0] == '1';
+  if (cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess) {
+    set_error("gsicp_gicp_create: no usable CUDA device (%s)", cudaGetErrorString(cudaGetLastError()));
+    delete h;
+    return nullptr;
+  }
+  return h;
+}
+
+void gsicp_gicp_destroy(gsicp_gicp* h) {
+  if (!h) return;
+  auto fr = [](Scratch& s) {
+    if (s.ptr) cudaFree(s.ptr);
+    s.ptr = nullptr;
+  };
+  for (Cloud* c : {&h->src, &h->tgt}) {
+    fr(c->xyz); fr(c->xyz_alt); fr(c->cov); fr(c->rots); fr(c->scales); fr(c->filter);
+    fr(c->grid.meta_buf); fr(c->grid.bbox_buf); fr(c->grid.cell_start); fr(c->grid.cursor); fr(c->grid.cell_of_pt);
+    fr(c->grid.pts); fr(c->grid.cub_tmp);
+  }
+  fr(h->corr); fr(h->sqd); fr(h->mahal); fr(h->partial); fr(h->red_out); fr(h->counter); fr(h->staging_dev);
+  if (h->h_red) cudaFreeHost(h->h_red);
+  if (h->h_stage) cudaFreeHost(h->h_stage);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  delete h;
+}
+
+#define H_CHECK(h) \
+  if (!(h)) { set_error("null handle"); return GSICP_EINVAL; }
+
+int gsicp_gicp_set_max_correspondence_distance(gsicp_gicp* h, double d) { H_CHECK(h); h->max_corr = d; return GSICP_OK; }
+int gsicp_gicp_set_max_knn_distance(gsicp_gicp* h, double d) { H_CHECK(h); h->knn_max = (float)d; return GSICP_OK; }
+int gsicp_gicp_set_correspondence_randomness(gsicp_gicp* h, int k) { H_CHECK(h); h->k = k; return GSICP_OK; }
+int gsicp_gicp_set_max_iterations(gsicp_gicp* h, int n) { H_CHECK(h); h->max_iterations = n; return GSICP_OK; }
+int gsicp_gicp_set_stream(gsicp_gicp* h, void* s) { H_CHECK(h); h->stream = (cudaStream_t)s; return GSICP_OK; }
+
+int gsicp_gicp_set_input_source(gsicp_gicp* h, const void* xyz, int n, int is_f32) {
+  H_CHECK(h);
+  h->corr_n = -1;
+  return set_cloud(h, h->src, xyz, n, is_f32, false);
+}
+int gsicp_gicp_set_input_target(gsicp_gicp* h, const void* xyz, int n, int is_f32) {
+  H_CHECK(h);
+  return set_cloud(h, h->tgt, xyz, n, is_f32, false);
+}
+int gsicp_gicp_set_input_source_device(gsicp_gicp* h, const float* d_xyz, int n) {
+  H_CHECK(h);
+  h->corr_n = -1;
+  return set_cloud(h, h->src, d_xyz, n, 1, true);
+}
+int gsicp_gicp_set_input_target_device(gsicp_gicp* h, const float* d_xyz, int n) {
+  H_CHECK(h);
+  return set_cloud(h, h->tgt, d_xyz, n, 1, true);
+}
+int gsicp_gicp_set_source_filter(gsicp_gicp* h, int nt, const int32_t* f, int n) { H_CHECK(h); return set_filter(h, h->src, nt, f, n); }
+int gsicp_gicp_set_target_filter(gsicp_gicp* h, int nt, const int32_t* f, int n) { H_CHECK(h); return set_filter(h, h->tgt, nt, f, n); }
+
+int gsicp_gicp_calculate_target_covariance_with_filter(gsicp_gicp* h) { H_CHECK(h); return compute_covariances(h, h->tgt, true, false); }
+int gsicp_gicp_calculate_source_covariance(gsicp_gicp* h) { H_CHECK(h); return compute_covariances(h, h->src, false, true); }
+int gsicp_gicp_calculate_target_covariance(gsicp_gicp* h) { H_CHECK(h); return compute_covariances(h, h->tgt, false, true); }
+
+int gsicp_gicp_set_source_covariances_fromqs(gsicp_gicp* h, const float* r, const float* s, int n) { H_CHECK(h); return covs_from_qs(h, h->src, r, s, n); }
+int gsicp_gicp_set_target_covariances_fromqs(gsicp_gicp* h, const float* r, const float* s, int n) { H_CHECK(h); return covs_from_qs(h, h->tgt, r, s, n); }
+
+int gsicp_gicp_align(gsicp_gicp* h, const float guess[16], float out[16]) {
+  H_CHECK(h);
+  if (!guess || !out) return GSICP_EINVAL;
+  // pcl::Registration::align: initCompute fails without a target
+  if (h->tgt.n == 0 || h->src.n == 0) {
+    set_error("align: %s cloud is empty", h->tgt.n == 0 ? "target" : "source");
+    return GSICP_ESTATE;
+  }
+  h->converged = false;
+  h->t_cov = h->t_lin = h->t_err = 0;
+  h->n_lin = h->n_err = 0;
+  // fgi:225-240: lazily compute missing covariances
+  if (h->src.cov_n != h->src.n) {
+    StageTimer tm(h, &h->t_cov);
+    if (int e = compute_covariances(h, h->src, true, false)) return e;
+    tm.stop();
+    h->corr_n = -1;
+  }
+  if (h->tgt.cov_n != h->tgt.n) {
+    if (int e = compute_covariances(h, h->tgt, false, true)) return e;
+  }
+  if (h->src.n == 0) {
+    set_error("align: no trackable source points");
+    return GSICP_ESTATE;
+  }
+  Iso x0;
+  for (int i = 0; i < 3; i++) {
+    for (int j = 0; j < 3; j++) x0.R[i][j] = (double)guess[4 * i + j];
+    x0.t[i] = (double)guess[4 * i + 3];
+  }
+  h->lm_lambda = -1.0;
+  int iters = 0;
+  for (int i = 0; i < h->max_iterations && !h->converged; i++) {
+    h->nr_iterations = i;
+    iters = i + 1;
+    Iso delta;
+    const int rc = step_lm(h, x0, delta);
+    if (rc < 0) return rc;
+    if (rc == 0) {
+      fprintf(stderr, "lm not converged!!\n");
+      break;
+    }
+    h->converged = is_converged(h, delta);
+  }
+  for (int i = 0; i < 3; i++) {
+    for (int j = 0; j < 3; j++) h->final_transformation[4 * i + j] = (float)x0.R[i][j];
+    h->final_transformation[4 * i + 3] = (float)x0.t[i];
+  }
+  h->final_transformation[12] = 0.f; h->final_transformation[13] = 0.f; h->final_transformation[14] = 0.f;
+  h->final_transformation[15] = 1.f;
+  std::memcpy(out, h->final_transformation, sizeof(float) * 16);
+  return iters;
+}
+
+int gsicp_gicp_has_converged(gsicp_gicp* h) { H_CHECK(h); return h->converged ? 1 : 0; }
+int gsicp_gicp_get_final_hessian(gsicp_gicp* h, double out[36]) { H_CHECK(h); std::memcpy(out, h->final_hessian, sizeof(double) * 36); return GSICP_OK; }
+
+int gsicp_gicp_source_size(gsicp_gicp* h) { H_CHECK(h); return h->src.n; }
+int gsicp_gicp_target_size(gsicp_gicp* h) { H_CHECK(h); return h->tgt.n; }
+int gsicp_gicp_source_rotationsq_size(gsicp_gicp* h) { H_CHECK(h); return h->src.rots_n; }
+int gsicp_gicp_target_rotationsq_size(gsicp_gicp* h) { H_CHECK(h); return h->tgt.rots_n; }
+int gsicp_gicp_source_scales_size(gsicp_gicp* h) { H_CHECK(h); return h->src.scales_n; }
+int gsicp_gicp_target_scales_size(gsicp_gicp* h) { H_CHECK(h); return h->tgt.scales_n; }
+int gsicp_gicp_get_source_rotationsq(gsicp_gicp* h, float* o) { H_CHECK(h); return copy_out(h, h->src.rots, (size_t)h->src.rots_n * 4, o); }
+int gsicp_gicp_get_target_rotationsq(gsicp_gicp* h, float* o) { H_CHECK(h); return copy_out(h, h->tgt.rots, (size_t)h->tgt.rots_n * 4, o); }
+int gsicp_gicp_get_source_scales(gsicp_gicp* h, float* o) { H_CHECK(h); return copy_out(h, h->src.scales, (size_t)h->src.scales_n * 4, o); }
+int gsicp_gicp_get_target_scales(gsicp_gicp* h, float* o) { H_CHECK(h); return copy_out(h, h->tgt.scales, (size_t)h->tgt.scales_n * 4, o); }
+int gsicp_gicp_get_source_covariances(gsicp_gicp* h, double* o) { H_CHECK(h); return copy_cov_out(h, h->src, o); }
+int gsicp_gicp_get_target_covariances(gsicp_gicp* h, double* o) { H_CHECK(h); return copy_cov_out(h, h->tgt, o); }
+
+int gsicp_gicp_get_source_correspondence(gsicp_gicp* h, int32_t* corr, float* sq_dist) {
+  H_CHECK(h);
+  if (h->corr_n != h->src.n) {
+    // reference prints "source and correspondence size mismatch" and returns stale vectors (fast_gicp.hpp:82-87)
+    fprintf(stderr, "source and correspondence size mismatch. Did you change src after align()?\n");
+    set_error("no correspondences for the current source cloud");
+    return GSICP_ESTATE;
+  }
+  if (int e = copy_out(h, h->corr, (size_t)h->src.n * 4, corr)) return e;
+  return copy_out(h, h->sqd, (size_t)h->src.n * 4, sq_dist);
+}
+
+static int pose_from16(const double p[16], Iso& x) {
+  if (!p) return GSICP_EINVAL;
+  for (int i = 0; i < 3; i++) {
+    for (int j = 0; j < 3; j++) x.R[i][j] = p[4 * i + j];
+    x.t[i] = p[4 * i + 3];
+  }
+  return GSICP_OK;
+}
+
+static int ready_for_linearize(gsicp_gicp* h) {
+  if (h->src.n == 0 || h->tgt.n == 0 || h->src.cov_n != h->src.n || h->tgt.cov_n != h->tgt.n) {
+    set_error("linearize: clouds or covariances missing (src %d/%d, tgt %d/%d)", h->src.cov_n, h->src.n, h->tgt.cov_n,
+              h->tgt.n);
+    return GSICP_ESTATE;
+  }
+  return GSICP_OK;
+}
+
+int gsicp_gicp_linearize(gsicp_gicp* h, const double pose[16], double Hout[36], double b[6], double* err) {
+  H_CHECK(h);
+  Iso x;
+  if (int e = pose_from16(pose, x)) return e;
+  if (int e = ready_for_linearize(h)) return e;
+  double H[6][6], bb[6], er;
+  if (int e = run_linearize(h, x, H, bb, &er)) return e;
+  if (Hout) std::memcpy(Hout, H, sizeof(H));
+  if (b) std::memcpy(b, bb, sizeof(bb));
+  if (err) *err = er;
+  return GSICP_OK;
+}
+
+int gsicp_gicp_compute_error(gsicp_gicp* h, const double pose[16], double* err) {
+  H_CHECK(h);
+  Iso x;
+  if (int e = pose_from16(pose, x)) return e;
+  if (int e = ready_for_linearize(h)) return e;
+  if (h->corr_n != h->src.n) {
+    set_error("compute_error: run linearize first");
+    return GSICP_ESTATE;
+  }
+  return run_error(h, x, err);
+}
+
+int gsicp_gicp_set_shard(gsicp_gicp* h, int count, int index, gsicp_allreduce_fn reduce, void* user) {
+  H_CHECK(h);
+  if (count < 1 || index < 0 || index >= count) return GSICP_EINVAL;
+  h->shard_count = count; h->shard_index = index; h->reduce = reduce; h->reduce_user = user;
+  h->corr_n = -1;
+  return GSICP_OK;
+}
+
+int gsicp_gicp_last_timing(gsicp_gicp* h, double out[5]) {
+  H_CHECK(h);
+  out[0] = h->t_cov; out[1] = h->t_lin; out[2] = h->t_err; out[3] = h->n_lin; out[4] = h->n_err;
+  return GSICP_OK;
+}
+
+}  // extern "C"

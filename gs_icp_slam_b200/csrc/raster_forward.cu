@@ -1,0 +1,531 @@
+// raster_forward.cu — forward pass of the B200 Gaussian-splat rasterizer.
+//
+// Replaces CudaRasterizer::Rasterizer::forward (DGR/cuda_rasterizer/rasterizer_impl.cu:201-347):
+//   preprocess -> scan -> duplicateWithKeys -> 64-bit radix sort -> identifyTileRanges -> render
+// with a pipeline re-designed around HBM traffic:
+//   preprocess (writes one 48-B splat record per visible Gaussian + its depth key)
+//   -> 32-bit depth sort of the P Gaussians (stable; ties keep index order)
+//   -> scan of tiles_touched in depth order -> emit (tile key u16/u32, Gaussian id) per instance
+//   -> STABLE radix sort on the tile key only (ceil(log2 tiles) bits, 2 passes instead of 6)
+//   -> tile ranges -> render.
+// Sorting by depth first and by tile second with a stable sort yields exactly the order of the
+// reference's single sort on (tile << 32 | depth bits): instances of a tile ordered by depth,
+// equal depths by Gaussian index — point_list is bit-identical (tests/test_raster_gpu.py).
+#include <cub/cub.cuh>
+#include <mutex>
+#include "host_common.h"
+#include "raster_common.cuh"
+
+namespace gsicp {
+
+// ------------------------------------------------------------------------------------------
+// preprocess: one thread per Gaussian (DGR/cuda_rasterizer/forward.cu:171-274)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ F3 sh_to_rgb(int idx, int deg, int max_coeffs, const float* __restrict__ means,
+                                        const float* __restrict__ campos, const float* __restrict__ shs,
+                                        uint8_t& clamp_mask) {
+  const F3 pos = {means[3 * idx], means[3 * idx + 1], means[3 * idx + 2]};
+  const F3 cam = {campos[0], campos[1], campos[2]};
+  F3 dir = pos - cam;
+  const float len = sqrtf(dot3(dir, dir));
+  dir = {dir.x / len, dir.y / len, dir.z / len};
+  const F3* sh = reinterpret_cast<const F3*>(shs) + (size_t)idx * max_coeffs;
+  F3 res = kShC0 * sh[0];
+  if (deg > 0) {
+    const float x = dir.x, y = dir.y, z = dir.z;
+    res = res - kShC1 * y * sh[1] + kShC1 * z * sh[2] - kShC1 * x * sh[3];
+    if (deg > 1) {
+      const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+      res = res + kShC2[0] * xy * sh[4] + kShC2[1] * yz * sh[5] + kShC2[2] * (2.0f * zz - xx - yy) * sh[6] +
+            kShC2[3] * xz * sh[7] + kShC2[4] * (xx - yy) * sh[8];
+      if (deg > 2) {
+        res = res + kShC3[0] * y * (3.0f * xx - yy) * sh[9] + kShC3[1] * xy * z * sh[10] +
+              kShC3[2] * y * (4.0f * zz - xx - yy) * sh[11] +
+              kShC3[3] * z * (2.0f * zz - 3.0f * xx - 3.0f * yy) * sh[12] +
+              kShC3[4] * x * (4.0f * zz - xx - yy) * sh[13] + kShC3[5] * z * (xx - yy) * sh[14] +
+              kShC3[6] * x * (xx - 3.0f * yy) * sh[15];
+      }
+    }
+  }
+  res = {res.x + 0.5f, res.y + 0.5f, res.z + 0.5f};
+  clamp_mask = (uint8_t)((res.x < 0.f ? 1 : 0) | (res.y < 0.f ? 2 : 0) | (res.z < 0.f ? 4 : 0));
+  return {fmaxf(res.x, 0.f), fmaxf(res.y, 0.f), fmaxf(res.z, 0.f)};
+}
+
+struct PreArgs {
+  int P, D, M, W, H, tiles_x, tiles_y;
+  float tan_fovx, tan_fovy, focal_x, focal_y, scale_modifier;
+  const float *means, *scales, *rots, *opac, *shs, *cov_pre, *col_pre, *view, *proj, *campos;
+  int prefiltered, shard_count, shard_index;
+};
+
+constexpr uint32_t kInvisibleKey = 0x7FFFFFFFu;  // sorts after every finite positive depth
+
+__global__ void __launch_bounds__(256)
+preprocess_kernel(PreArgs a, int32_t* __restrict__ radii, uint8_t* __restrict__ is_used, Splat* __restrict__ splats,
+                  uint8_t* __restrict__ clamped, uint32_t* __restrict__ depth_key, uint32_t* __restrict__ ident,
+                  uint32_t* __restrict__ tiles_touched) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= a.P) return;
+  radii[idx] = 0;
+  tiles_touched[idx] = 0;
+  depth_key[idx] = kInvisibleKey;
+  ident[idx] = idx;
+
+  const float3 p = make_float3(a.means[3 * idx], a.means[3 * idx + 1], a.means[3 * idx + 2]);
+  const float3 pv = xform_point_4x3(p, a.view);
+  if (pv.z <= 0.2f) {  // near cull only; no x/y frustum test (auxiliary.h:159)
+    if (a.prefiltered) {
+      printf("Point is filtered although prefiltered is set. This shouldn't happen!");
+      __trap();
+    }
+    return;
+  }
+  const float4 ph = xform_point_4x4(p, a.proj);
+  const float pw = 1.0f / (ph.w + 0.0000001f);
+  const float3 pp = make_float3(ph.x * pw, ph.y * pw, ph.z * pw);
+
+  float cov3[6];
+  if (a.cov_pre) {
+#pragma unroll
+    for (int i = 0; i < 6; i++) cov3[i] = a.cov_pre[6 * (size_t)idx + i];
+  } else {
+    const float3 s = make_float3(a.scales[3 * idx], a.scales[3 * idx + 1], a.scales[3 * idx + 2]);
+    const float4 q = reinterpret_cast<const float4*>(a.rots)[idx];
+    cov3d_from_scale_rot(s, a.scale_modifier, q, cov3);
+  }
+
+  const Ewa e = ewa_project(p, a.focal_x, a.focal_y, a.tan_fovx, a.tan_fovy, cov3, a.view);
+  const float cxx = e.cov.m[0][0] + 0.3f;  // low-pass: at least one pixel wide
+  const float cxy = e.cov.m[0][1];
+  const float czx = e.cov.m[0][2];
+  const float cyy = e.cov.m[1][1] + 0.3f;
+  const float cyz = e.cov.m[1][2];
+
+  const float det = (cxx * cyy - cxy * cxy);
+  if (det == 0.0f) return;
+  const float det_inv = 1.f / det;
+  const float conx = cyy * det_inv, cony = -cxy * det_inv, conz = cxx * det_inv;
+
+  const float mid = 0.5f * (cxx + cyy);
+  const float lambda1 = mid + sqrtf(fmaxf(0.1f, mid * mid - det));
+  const float lambda2 = mid - sqrtf(fmaxf(0.1f, mid * mid - det));
+  const float my_radius = ceilf(3.f * sqrtf(fmaxf(lambda1, lambda2)));
+  const float px = ndc_to_pix(pp.x, a.W), py = ndc_to_pix(pp.y, a.H);
+  int x0, y0, x1, y1;
+  tile_rect(px, py, (int)my_radius, a.tiles_x, a.tiles_y, x0, y0, x1, y1);
+  if ((x1 - x0) * (y1 - y0) == 0) return;
+
+  F3 rgb;
+  uint8_t cm = 0;
+  if (a.col_pre) {
+    rgb = {a.col_pre[3 * idx], a.col_pre[3 * idx + 1], a.col_pre[3 * idx + 2]};
+  } else {
+    rgb = sh_to_rgb(idx, a.D, a.M, a.means, a.campos, a.shs, cm);
+  }
+  clamped[idx] = cm;
+
+  Splat s;
+  s.a = make_float4(px, py, conx, cony);
+  s.b = make_float4(conz, a.opac[idx], czx, cyz);
+  s.c = make_float4(rgb.x, rgb.y, rgb.z, pv.z);
+  splats[idx] = s;
+  radii[idx] = (int)my_radius;
+  depth_key[idx] = __float_as_uint(pv.z);
+  is_used[idx] = 1;
+
+  // tile instances this rank owns (tile % shard_count == shard_index)
+  uint32_t n = (uint32_t)((y1 - y0) * (x1 - x0));
+  if (a.shard_count > 1) {
+    n = 0;
+    for (int y = y0; y < y1; y++)
+      for (int x = x0; x < x1; x++) n += ((y * a.tiles_x + x) % a.shard_count == a.shard_index);
+  }
+  tiles_touched[idx] = n;
+}
+
+// tiles_touched gathered into depth order, ready for the prefix sum
+__global__ void gather_counts_kernel(int P, const uint32_t* __restrict__ order, const uint32_t* __restrict__ tiles_touched,
+                                     uint32_t* __restrict__ out) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < P) out[s] = tiles_touched[order[s]];
+}
+
+// One thread per depth-sorted Gaussian: write (tile, id) for every owned tile of its rectangle
+// (reference: duplicateWithKeys, rasterizer_impl.cu:70-111, but keyed by tile only).
+template <typename KeyT>
+__global__ void emit_instances_kernel(int P, const uint32_t* __restrict__ order, const uint32_t* __restrict__ offsets,
+                                      const uint32_t* __restrict__ tiles_touched, const Splat* __restrict__ splats,
+                                      const int32_t* __restrict__ radii, int tiles_x, int tiles_y, int shard_count,
+                                      int shard_index, KeyT* __restrict__ keys, uint32_t* __restrict__ vals) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= P) return;
+  const uint32_t g = order[s];
+  if (tiles_touched[g] == 0) return;
+  uint32_t off = (s == 0) ? 0u : offsets[s - 1];
+  const float4 a = splats[g].a;
+  int x0, y0, x1, y1;
+  tile_rect(a.x, a.y, radii[g], tiles_x, tiles_y, x0, y0, x1, y1);
+  for (int y = y0; y < y1; y++) {
+    for (int x = x0; x < x1; x++) {
+      const int t = y * tiles_x + x;
+      if (shard_count > 1 && (t % shard_count) != shard_index) continue;
+      keys[off] = (KeyT)t;
+      vals[off] = g;
+      off++;
+    }
+  }
+}
+
+template <typename KeyT>
+__global__ void tile_ranges_kernel(int R, const KeyT* __restrict__ keys, uint2* __restrict__ ranges) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= R) return;
+  const uint32_t cur = keys[i];
+  if (i == 0) {
+    ranges[cur].x = 0;
+  } else {
+    const uint32_t prev = keys[i - 1];
+    if (cur != prev) {
+      ranges[prev].y = i;
+      ranges[cur].x = i;
+    }
+  }
+  if (i == R - 1) ranges[cur].y = R;
+}
+
+// ------------------------------------------------------------------------------------------
+// render forward: one CTA per 16x16 tile, each warp owns an 8x4 sub-tile.
+//
+// Per batch of 256 tile instances the CTA stages the 48-B splat records in shared memory with
+// 128-bit loads (one instance per thread).  Each warp then culls the batch against its own 8x4
+// pixel rectangle — lane l tests instance 32*chunk+l: the axis-aligned bounding box of the
+// ellipse {alpha >= 1/255} — and only the survivors (ballot mask) are evaluated by all 32 lanes.
+// Culled instances are exactly those the reference skips for every pixel of the sub-tile
+// (power > 0 or alpha < 1/255, forward.cu:359-366), so the blend result is unchanged while the
+// pixel-Gaussian pair count drops by the ratio (bounding-square tiles) / (ellipse ∩ sub-tiles).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool subtile_hit(const float4 a, const float4 b, float wx0, float wy0) {
+  const float A = a.z, B = a.w, C = b.x, o = b.y;
+  const float det = A * C - B * B;
+  const float t255 = 255.f * o;
+  if (!(t255 >= 0.999f)) return false;  // alpha = o * exp(power <= 0) can never reach 1/255
+  if (!(A > 0.f && C > 0.f && det > 0.f)) return true;  // not an ellipse: do not cull
+  const float tau = fmaxf(__logf(t255), 0.f) * 1.001f + 2e-3f;  // power >= -tau  <=>  alpha >= 1/255 (with margin)
+  const float inv = 2.f * tau / det;
+  const float hx = sqrtf(inv * C) * 1.0005f + 1e-3f;
+  const float hy = sqrtf(inv * A) * 1.0005f + 1e-3f;
+  return (a.x + hx >= wx0) && (a.x - hx <= wx0 + 7.f) && (a.y + hy >= wy0) && (a.y - hy <= wy0 + 3.f);
+}
+
+template <bool kCull>
+__global__ void __launch_bounds__(kTilePixels)
+render_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H,
+                      int tiles_x, const Splat* __restrict__ splats, const float* __restrict__ bg,
+                      float* __restrict__ out_color, float* __restrict__ out_depth, float* __restrict__ final_T,
+                      uint32_t* __restrict__ n_contrib, int shard_count, int shard_index) {
+  const int tile = blockIdx.x;
+  if (shard_count > 1 && (tile % shard_count) != shard_index) return;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tile_x = tile % tiles_x, tile_y = tile / tiles_x;
+  const int wx0 = tile_x * kTile + (warp & 1) * 8, wy0 = tile_y * kTile + (warp >> 1) * 4;
+  const int px = wx0 + (lane & 7), py = wy0 + (lane >> 3);
+  const bool inside = px < W && py < H;
+  const float pxf = (float)px, pyf = (float)py;
+
+  __shared__ float4 sA[kTilePixels], sB[kTilePixels], sC[kTilePixels];
+
+  const uint2 range = ranges[tile];
+  const int total = (int)(range.y - range.x);
+  bool done = !inside;
+  float T = 1.f, Cr = 0.f, Cg = 0.f, Cb = 0.f, D = 0.f;
+  uint32_t last = 0;
+
+  for (int base = 0; base < total; base += kTilePixels) {
+    if (__syncthreads_count(done) == kTilePixels) break;
+    const int n = min(kTilePixels, total - base);
+    if (tid < n) {
+      const uint32_t g = point_list[range.x + base + tid];
+      const Splat* sp = splats + g;
+      sA[tid] = __ldg(&sp->a);
+      sB[tid] = __ldg(&sp->b);
+      sC[tid] = __ldg(&sp->c);
+    }
+    __syncthreads();
+    if (__all_sync(0xffffffffu, done)) continue;
+
+    for (int c0 = 0; c0 < n; c0 += 32) {
+      uint32_t mask;
+      if (kCull) {
+        const int j = c0 + lane;
+        const bool hit = (j < n) && subtile_hit(sA[j], sB[j], (float)wx0, (float)wy0);
+        mask = __ballot_sync(0xffffffffu, hit);
+      } else {
+        mask = (n - c0 >= 32) ? 0xffffffffu : ((1u << (n - c0)) - 1u);
+      }
+      while (mask) {
+        const int bit = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const int j = c0 + bit;
+        if (done) continue;
+        const float4 a = sA[j], b = sB[j];
+        const float dx = a.x - pxf, dy = a.y - pyf;
+        const float power = -0.5f * (a.z * dx * dx + b.x * dy * dy) - a.w * dx * dy;
+        if (power > 0.0f) continue;
+        const float alpha = fminf(0.99f, b.y * expf(power));
+        if (alpha < 1.0f / 255.0f) continue;
+        const float test_T = T * (1 - alpha);
+        if (test_T < 0.0001f) {
+          done = true;  // colour and depth both stop here (forward.cu:367-383,392-393)
+          continue;
+        }
+        const float4 c = sC[j];
+        Cr += c.x * alpha * T;
+        Cg += c.y * alpha * T;
+        Cb += c.z * alpha * T;
+        // depth conditioned on the pixel offset through the z cross-covariances (forward.cu:395-399)
+        const float dcond = c.w - (b.z * a.z + b.w * a.w) * dx - (b.z * a.w + b.w * b.x) * dy;
+        D += dcond * alpha * T;
+        T = test_T;
+        last = (uint32_t)(base + j + 1);
+      }
+      if (__all_sync(0xffffffffu, done)) break;
+    }
+  }
+
+  if (inside) {
+    const int pix = py * W + px;
+    final_T[pix] = T;
+    n_contrib[pix] = last;
+    out_depth[pix] = D + T * 15.f;  // background depth 15 m (forward.cu:419-421)
+    const size_t HW = (size_t)H * W;
+    out_color[0 * HW + pix] = Cr + T * bg[0];
+    out_color[1 * HW + pix] = Cg + T * bg[1];
+    out_color[2 * HW + pix] = Cb + T * bg[2];
+  }
+}
+
+__global__ void mark_visible_kernel(int P, const float* __restrict__ means, const float* __restrict__ view,
+                                    uint8_t* __restrict__ present) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= P) return;
+  const float3 p = make_float3(means[3 * idx], means[3 * idx + 1], means[3 * idx + 2]);
+  present[idx] = xform_point_4x3(p, view).z > 0.2f;
+}
+
+__global__ void copy_ranges_kernel(int tiles, const uint2* __restrict__ ranges, uint32_t* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < tiles) {
+    out[2 * i] = ranges[i].x;
+    out[2 * i + 1] = ranges[i].y;
+  }
+}
+
+// Library-internal scratch (not needed by backward).  One rasterization in flight per process,
+// like the reference (which launches everything on the legacy default stream).
+struct FwdScratch {
+  std::mutex mu;
+  Scratch per_gaussian, per_instance, cub_tmp;
+  int* h_count = nullptr;  // pinned
+};
+static FwdScratch g_fwd;
+
+static uint32_t bits_for(uint32_t n) {  // smallest b with (1<<b) >= n
+  uint32_t b = 0;
+  while ((1ull << b) < n) b++;
+  return b ? b : 1;
+}
+
+int g_render_cull = 1;  // test hook: 0 renders without sub-tile culling (must give identical output)
+
+}  // namespace gsicp
+
+using namespace gsicp;
+
+extern "C" int gsicp_raster_forward(const gsicp_raster_args* args, float* d_out_color, float* d_out_depth,
+                                    int32_t* d_radii, uint8_t* d_is_used, gsicp_alloc_fn geom_alloc,
+                                    gsicp_alloc_fn binning_alloc, gsicp_alloc_fn image_alloc, void* user,
+                                    void* stream_v) {
+  if (!args || !geom_alloc || !binning_alloc || !image_alloc) {
+    set_error("gsicp_raster_forward: null argument");
+    return GSICP_EINVAL;
+  }
+  const int P = args->P, W = args->width, H = args->height;
+  if (P < 0 || W <= 0 || H <= 0) {
+    set_error("gsicp_raster_forward: bad sizes P=%d W=%d H=%d", P, W, H);
+    return GSICP_EINVAL;
+  }
+  if (!args->d_shs && !args->d_colors_precomp && P > 0) {
+    set_error("gsicp_raster_forward: provide SHs or precomputed colours");
+    return GSICP_EINVAL;
+  }
+  if (!args->d_cov3D_precomp && (!args->d_scales || !args->d_rotations) && P > 0) {
+    set_error("gsicp_raster_forward: provide scale/rotation or precomputed 3D covariance");
+    return GSICP_EINVAL;
+  }
+  cudaStream_t stream = (cudaStream_t)stream_v;
+  const int shard_count = args->tile_shard_count > 1 ? args->tile_shard_count : 1;
+  const int shard_index = shard_count > 1 ? args->tile_shard_index : 0;
+  const int tiles_x = (W + kTile - 1) / kTile, tiles_y = (H + kTile - 1) / kTile;
+  const int tiles = tiles_x * tiles_y;
+  const size_t N = (size_t)W * H;
+
+  char* geom_p = (char*)geom_alloc(GeomState::bytes(P), user);
+  char* img_p = (char*)image_alloc(ImgState::bytes(N, tiles), user);
+  if (!geom_p || !img_p) {
+    set_error("gsicp_raster_forward: workspace callback returned NULL");
+    return GSICP_ENOMEM;
+  }
+  GeomState geom = GeomState::from(geom_p, P);
+  ImgState img = ImgState::from(img_p, N, tiles);
+
+  std::lock_guard<std::mutex> lock(g_fwd.mu);
+  if (!g_fwd.h_count) GSICP_CUDA(cudaMallocHost(&g_fwd.h_count, sizeof(int)));
+
+  int R = 0;
+  uint32_t *depth_key = nullptr, *ident = nullptr, *depth_sorted = nullptr, *order = nullptr, *tiles_touched = nullptr,
+           *counts = nullptr, *offsets = nullptr;
+  if (P > 0) {
+    // per-Gaussian scratch: 7 x u32[P]
+    const size_t stride = ((size_t)P * 4 + 127) & ~size_t(127);
+    if (int e = g_fwd.per_gaussian.ensure(7 * stride)) return e;
+    char* base = g_fwd.per_gaussian.as<char>();
+    depth_key = (uint32_t*)(base + 0 * stride);
+    ident = (uint32_t*)(base + 1 * stride);
+    depth_sorted = (uint32_t*)(base + 2 * stride);
+    order = (uint32_t*)(base + 3 * stride);
+    tiles_touched = (uint32_t*)(base + 4 * stride);
+    counts = (uint32_t*)(base + 5 * stride);
+    offsets = (uint32_t*)(base + 6 * stride);
+
+    PreArgs pa;
+    pa.P = P; pa.D = args->D; pa.M = args->M; pa.W = W; pa.H = H; pa.tiles_x = tiles_x; pa.tiles_y = tiles_y;
+    pa.tan_fovx = args->tan_fovx; pa.tan_fovy = args->tan_fovy;
+    pa.focal_y = H / (2.0f * args->tan_fovy);
+    pa.focal_x = W / (2.0f * args->tan_fovx);
+    pa.scale_modifier = args->scale_modifier;
+    pa.means = args->d_means3D; pa.scales = args->d_scales; pa.rots = args->d_rotations; pa.opac = args->d_opacities;
+    pa.shs = args->d_shs; pa.cov_pre = args->d_cov3D_precomp; pa.col_pre = args->d_colors_precomp;
+    pa.view = args->d_viewmatrix; pa.proj = args->d_projmatrix; pa.campos = args->d_campos;
+    pa.prefiltered = args->prefiltered; pa.shard_count = shard_count; pa.shard_index = shard_index;
+    const int grid = (P + 255) / 256;
+    GSICP_LAUNCH(preprocess_kernel, grid, 256, 0, stream, pa, d_radii, d_is_used, geom.splats, geom.clamped, depth_key,
+                 ident, tiles_touched);
+    if (args->debug) GSICP_CUDA(cudaStreamSynchronize(stream));
+
+    // depth sort (31 significant bits: positive floats and the invisible sentinel)
+    size_t tmp1 = 0, tmp2 = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp1, depth_key, depth_sorted, ident, order, P, 0, 31, stream);
+    cub::DeviceScan::InclusiveSum(nullptr, tmp2, counts, offsets, P, stream);
+    if (int e = g_fwd.cub_tmp.ensure(tmp1 > tmp2 ? tmp1 : tmp2)) return e;
+    size_t tmp = g_fwd.cub_tmp.cap;
+    GSICP_CUDA(cub::DeviceRadixSort::SortPairs(g_fwd.cub_tmp.ptr, tmp, depth_key, depth_sorted, ident, order, P, 0, 31,
+                                               stream));
+    g_launches.fetch_add(4, std::memory_order_relaxed);
+    GSICP_LAUNCH(gather_counts_kernel, grid, 256, 0, stream, P, order, tiles_touched, counts);
+    tmp = g_fwd.cub_tmp.cap;
+    GSICP_CUDA(cub::DeviceScan::InclusiveSum(g_fwd.cub_tmp.ptr, tmp, counts, offsets, P, stream));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+
+    // The Python API returns num_rendered as a host int (DGR/diff_gaussian_rasterization/__init__.py:96),
+    // and the instance buffers are sized by it: one 4-byte D2H + sync, as in rasterizer_impl.cu:286-287.
+    GSICP_CUDA(cudaMemcpyAsync(g_fwd.h_count, offsets + (P - 1), sizeof(int), cudaMemcpyDeviceToHost, stream));
+    GSICP_CUDA(cudaStreamSynchronize(stream));
+    R = *g_fwd.h_count;
+    if (R < 0) {
+      set_error("gsicp_raster_forward: instance count overflow");
+      return GSICP_EINVAL;
+    }
+  }
+
+  char* bin_p = (char*)binning_alloc(BinState::bytes(R), user);
+  if (!bin_p) {
+    set_error("gsicp_raster_forward: binning callback returned NULL");
+    return GSICP_ENOMEM;
+  }
+  BinState bin = BinState::from(bin_p, R);
+
+  GSICP_CUDA(cudaMemsetAsync(img.ranges, 0, sizeof(uint2) * tiles, stream));
+  if (R > 0) {
+    const bool k16 = tiles <= 65536;
+    const size_t ksz = k16 ? 2 : 4;
+    const size_t kstride = ((size_t)R * ksz + 127) & ~size_t(127);
+    const size_t vstride = ((size_t)R * 4 + 127) & ~size_t(127);
+    if (int e = g_fwd.per_instance.ensure(2 * kstride + vstride)) return e;
+    char* base = g_fwd.per_instance.as<char>();
+    void* keys_in = base;
+    void* keys_out = base + kstride;
+    uint32_t* vals_in = (uint32_t*)(base + 2 * kstride);
+    const int gridP = (P + 255) / 256, gridR = (R + 255) / 256;
+    const int bits = (int)bits_for((uint32_t)tiles);
+    size_t tmp = 0;
+    if (k16) {
+      GSICP_LAUNCH(emit_instances_kernel<uint16_t>, gridP, 256, 0, stream, P, order, offsets, tiles_touched, geom.splats,
+                   d_radii, tiles_x, tiles_y, shard_count, shard_index, (uint16_t*)keys_in, vals_in);
+      cub::DeviceRadixSort::SortPairs(nullptr, tmp, (uint16_t*)keys_in, (uint16_t*)keys_out, vals_in, bin.point_list, R, 0,
+                                      bits, stream);
+      if (int e = g_fwd.cub_tmp.ensure(tmp)) return e;
+      tmp = g_fwd.cub_tmp.cap;
+      GSICP_CUDA(cub::DeviceRadixSort::SortPairs(g_fwd.cub_tmp.ptr, tmp, (uint16_t*)keys_in, (uint16_t*)keys_out, vals_in,
+                                                 bin.point_list, R, 0, bits, stream));
+      GSICP_LAUNCH(tile_ranges_kernel<uint16_t>, gridR, 256, 0, stream, R, (const uint16_t*)keys_out, img.ranges);
+    } else {
+      GSICP_LAUNCH(emit_instances_kernel<uint32_t>, gridP, 256, 0, stream, P, order, offsets, tiles_touched, geom.splats,
+                   d_radii, tiles_x, tiles_y, shard_count, shard_index, (uint32_t*)keys_in, vals_in);
+      cub::DeviceRadixSort::SortPairs(nullptr, tmp, (uint32_t*)keys_in, (uint32_t*)keys_out, vals_in, bin.point_list, R, 0,
+                                      bits, stream);
+      if (int e = g_fwd.cub_tmp.ensure(tmp)) return e;
+      tmp = g_fwd.cub_tmp.cap;
+      GSICP_CUDA(cub::DeviceRadixSort::SortPairs(g_fwd.cub_tmp.ptr, tmp, (uint32_t*)keys_in, (uint32_t*)keys_out, vals_in,
+                                                 bin.point_list, R, 0, bits, stream));
+      GSICP_LAUNCH(tile_ranges_kernel<uint32_t>, gridR, 256, 0, stream, R, (const uint32_t*)keys_out, img.ranges);
+    }
+    g_launches.fetch_add(3, std::memory_order_relaxed);
+    if (args->debug) GSICP_CUDA(cudaStreamSynchronize(stream));
+  }
+
+  if (P > 0) {
+    if (g_render_cull) {
+      GSICP_LAUNCH(render_forward_kernel<true>, tiles, kTilePixels, 0, stream, img.ranges, bin.point_list, W, H, tiles_x,
+                   geom.splats, args->d_background, d_out_color, d_out_depth, img.final_T, img.n_contrib, shard_count,
+                   shard_index);
+    } else {
+      GSICP_LAUNCH(render_forward_kernel<false>, tiles, kTilePixels, 0, stream, img.ranges, bin.point_list, W, H, tiles_x,
+                   geom.splats, args->d_background, d_out_color, d_out_depth, img.final_T, img.n_contrib, shard_count,
+                   shard_index);
+    }
+    if (args->debug) GSICP_CUDA(cudaStreamSynchronize(stream));
+  }
+  GSICP_CUDA(cudaGetLastError());
+  return R;
+}
+
+extern "C" int gsicp_raster_export_binning(const gsicp_raster_args* args, int num_rendered, const void* d_binning,
+                                           const void* d_image, uint32_t* d_point_list, uint32_t* d_ranges,
+                                           void* stream_v) {
+  if (!args || !d_binning || !d_image) return GSICP_EINVAL;
+  cudaStream_t stream = (cudaStream_t)stream_v;
+  const int W = args->width, H = args->height;
+  const int tiles_x = (W + kTile - 1) / kTile, tiles_y = (H + kTile - 1) / kTile, tiles = tiles_x * tiles_y;
+  BinState bin = BinState::from((char*)d_binning, num_rendered);
+  ImgState img = ImgState::from((char*)d_image, (size_t)W * H, tiles);
+  if (d_point_list && num_rendered > 0)
+    GSICP_CUDA(cudaMemcpyAsync(d_point_list, bin.point_list, sizeof(uint32_t) * (size_t)num_rendered,
+                               cudaMemcpyDeviceToDevice, stream));
+  if (d_ranges) GSICP_LAUNCH(copy_ranges_kernel, (tiles + 255) / 256, 256, 0, stream, tiles, img.ranges, d_ranges);
+  GSICP_CUDA(cudaGetLastError());
+  return GSICP_OK;
+}
+
+extern "C" int gsicp_mark_visible(int P, const float* d_means3D, const float* d_viewmatrix, const float* d_projmatrix,
+                                  uint8_t* d_present, void* stream_v) {
+  (void)d_projmatrix;
+  if (P < 0) return GSICP_EINVAL;
+  if (P == 0) return GSICP_OK;
+  GSICP_LAUNCH(mark_visible_kernel, (P + 255) / 256, 256, 0, (cudaStream_t)stream_v, P, d_means3D, d_viewmatrix,
+               d_present);
+  GSICP_CUDA(cudaGetLastError());
+  return GSICP_OK;
+}
+
+extern "C" void gsicp_test_set_render_cull(int on) { gsicp::g_render_cull = on; }

@@ -1,0 +1,182 @@
+"""Host side of the rasterizer: torch tensors in, C-ABI calls, torch tensors out.
+
+Mirrors the three functions the reference's extension module exports
+(submodules/diff-gaussian-rasterization/ext.cpp:15-19, rasterize_points.cu:35-227):
+`rasterize_gaussians`, `rasterize_gaussians_backward`, `mark_visible` — same argument order,
+same return tuples, same "empty tensor means not provided" convention.  PyTorch is used only
+for device memory and the current stream; every kernel is ours (libgsicp_b200.so).
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import RasterArgs, check, lib
+
+NUM_CHANNELS = 3
+
+# Tile sharding for multi-GPU runs: (count, index); set by gs_icp_slam_b200.sharding.
+_tile_shard = (1, 0)
+
+
+def set_tile_shard(count, index):
+    global _tile_shard
+    if count < 1 or not (0 <= index < count):
+        raise ValueError("bad tile shard")
+    _tile_shard = (int(count), int(index))
+
+
+def _ptr(t):
+    """Device pointer of a tensor, or None for the reference's 'not provided' empty tensor."""
+    if t is None or t.numel() == 0:
+        return None
+    return t.data_ptr()
+
+
+def _f32c(t, device):
+    if t is None or t.numel() == 0:
+        return None
+    if t.device != device:
+        raise ValueError(f"tensor on {t.device}, expected {device}")
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+class _Buffers:
+    """The three resizable byte buffers (reference: resizeFunctional, rasterize_points.cu:27-33)."""
+
+    def __init__(self, device):
+        self.device = device
+        self.t = {}
+        self.cbs = []
+
+    def cb(self, key):
+        def alloc(nbytes, _user):
+            t = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+            self.t[key] = t
+            return t.data_ptr()
+
+        f = _lib.ALLOC_FN(alloc)
+        self.cbs.append(f)
+        return f
+
+
+def _make_args(P, D, M, H, W, tanx, tany, scale_mod, prefiltered, debug, bg, means3D, sh, colors, opacity, scales,
+               rotations, cov3D, view, proj, campos):
+    a = RasterArgs()
+    a.P, a.D, a.M, a.width, a.height = P, D, M, W, H
+    a.tan_fovx, a.tan_fovy, a.scale_modifier = tanx, tany, scale_mod
+    a.prefiltered, a.debug = int(bool(prefiltered)), int(bool(debug))
+    a.d_background = _ptr(bg)
+    a.d_means3D = _ptr(means3D)
+    a.d_shs = _ptr(sh)
+    a.d_colors_precomp = _ptr(colors)
+    a.d_opacities = _ptr(opacity)
+    a.d_scales = _ptr(scales)
+    a.d_rotations = _ptr(rotations)
+    a.d_cov3D_precomp = _ptr(cov3D)
+    a.d_viewmatrix = _ptr(view)
+    a.d_projmatrix = _ptr(proj)
+    a.d_campos = _ptr(campos)
+    a.tile_shard_count, a.tile_shard_index = _tile_shard
+    return a
+
+
+def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations, scale_modifier, cov3D_precomp,
+                        viewmatrix, projmatrix, tan_fovx, tan_fovy, image_height, image_width, sh, degree, campos,
+                        prefiltered, debug):
+    """_C.rasterize_gaussians (rasterize_points.cu:35-121).
+
+    Returns (num_rendered, out_depth[1,H,W], out_color[3,H,W], radii[P] int32, is_used[P] bool,
+    geomBuffer, binningBuffer, imgBuffer)."""
+    if means3D.ndimension() != 2 or means3D.size(1) != 3:
+        raise RuntimeError("means3D must have dimensions (num_points, 3)")
+    if not means3D.is_cuda:
+        raise RuntimeError("gs_icp_slam_b200 rasterizer: means3D must be a CUDA tensor (no CPU fallback)")
+    dev = means3D.device
+    P, H, W = means3D.size(0), int(image_height), int(image_width)
+    with torch.cuda.device(dev):
+        out_depth = torch.zeros((1, H, W), dtype=torch.float32, device=dev)
+        out_color = torch.zeros((NUM_CHANNELS, H, W), dtype=torch.float32, device=dev)
+        radii = torch.zeros((P,), dtype=torch.int32, device=dev)
+        is_used = torch.zeros((P,), dtype=torch.bool, device=dev)
+        bufs = _Buffers(dev)
+        rendered = 0
+        if P != 0:
+            M = sh.size(1) if sh.numel() != 0 else 0
+            keep = [_f32c(x, dev) for x in (background, means3D, sh, colors, opacity, scales, rotations, cov3D_precomp,
+                                            viewmatrix, projmatrix, campos)]
+            bg, m3, shc, col, opa, sc, rot, cov, view, proj, cam = keep
+            args = _make_args(P, int(degree), M, H, W, float(tan_fovx), float(tan_fovy), float(scale_modifier),
+                              prefiltered, debug, bg, m3, shc, col, opa, sc, rot, cov, view, proj, cam)
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            rendered = check(
+                lib.gsicp_raster_forward(C.byref(args), out_color.data_ptr(), out_depth.data_ptr(), radii.data_ptr(),
+                                         is_used.data_ptr(), bufs.cb("geom"), bufs.cb("binning"), bufs.cb("img"), None,
+                                         stream), "gsicp_raster_forward")
+        empty = torch.empty(0, dtype=torch.uint8, device=dev)
+        return (rendered, out_depth, out_color, radii, is_used, bufs.t.get("geom", empty), bufs.t.get("binning", empty),
+                bufs.t.get("img", empty))
+
+
+def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rotations, scale_modifier, cov3D_precomp,
+                                 viewmatrix, projmatrix, tan_fovx, tan_fovy, dL_dout_depth, dL_dout_color, sh, degree,
+                                 campos, geomBuffer, R, binningBuffer, imageBuffer, debug):
+    """_C.rasterize_gaussians_backward (rasterize_points.cu:123-206).
+
+    Returns (dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations)."""
+    dev = means3D.device
+    P = means3D.size(0)
+    H, W = dL_dout_color.size(1), dL_dout_color.size(2)
+    M = sh.size(1) if sh.numel() != 0 else 0
+    with torch.cuda.device(dev):
+        z = lambda *s: torch.zeros(s, dtype=torch.float32, device=dev)
+        dL_dmeans3D, dL_dmeans2D, dL_dcolors = z(P, 3), z(P, 3), z(P, NUM_CHANNELS)
+        dL_dopacity, dL_dcov3D, dL_dsh = z(P, 1), z(P, 6), z(P, M, 3)
+        dL_dscales, dL_drotations = z(P, 3), z(P, 4)
+        if P != 0:
+            work = torch.zeros(int(lib.gsicp_raster_backward_work_bytes(P)) // 4, dtype=torch.float32, device=dev)
+            keep = [_f32c(x, dev) for x in (background, means3D, sh, colors, None, scales, rotations, cov3D_precomp,
+                                            viewmatrix, projmatrix, campos, dL_dout_color, dL_dout_depth)]
+            bg, m3, shc, col, _, sc, rot, cov, view, proj, cam, gcol, gdep = keep
+            args = _make_args(P, int(degree), M, H, W, float(tan_fovx), float(tan_fovy), float(scale_modifier), False,
+                              debug, bg, m3, shc, col, None, sc, rot, cov, view, proj, cam)
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            radii_c = radii.contiguous()
+            check(
+                lib.gsicp_raster_backward(C.byref(args), int(R), radii_c.data_ptr(), geomBuffer.data_ptr(),
+                                          binningBuffer.data_ptr(), imageBuffer.data_ptr(), gcol.data_ptr(),
+                                          gdep.data_ptr(), dL_dmeans2D.data_ptr(), dL_dcolors.data_ptr(),
+                                          dL_dopacity.data_ptr(), dL_dmeans3D.data_ptr(), dL_dcov3D.data_ptr(),
+                                          _ptr(dL_dsh), dL_dscales.data_ptr(), dL_drotations.data_ptr(),
+                                          work.data_ptr(), stream), "gsicp_raster_backward")
+        return dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations
+
+
+def mark_visible(means3D, viewmatrix, projmatrix):
+    """_C.mark_visible (rasterize_points.cu:208-227)."""
+    dev = means3D.device
+    P = means3D.size(0)
+    present = torch.zeros((P,), dtype=torch.bool, device=dev)
+    if P != 0:
+        with torch.cuda.device(dev):
+            m3, view, proj = (_f32c(x, dev) for x in (means3D, viewmatrix, projmatrix))
+            check(lib.gsicp_mark_visible(P, m3.data_ptr(), view.data_ptr(), proj.data_ptr(), present.data_ptr(),
+                                         torch.cuda.current_stream(dev).cuda_stream), "gsicp_mark_visible")
+    return present
+
+
+def export_binning(num_rendered, height, width, binningBuffer, imageBuffer):
+    """Test hook: (point_list uint32[R] as int64 tensor, ranges int64[tiles,2]) from the saved state."""
+    dev = imageBuffer.device
+    tiles = ((width + 15) // 16) * ((height + 15) // 16)
+    a = RasterArgs()
+    a.width, a.height = width, height
+    pl = torch.zeros(max(num_rendered, 1), dtype=torch.int32, device=dev)
+    rg = torch.zeros(tiles * 2, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.gsicp_raster_export_binning(C.byref(a), int(num_rendered), binningBuffer.data_ptr(),
+                                              imageBuffer.data_ptr(), pl.data_ptr(), rg.data_ptr(),
+                                              torch.cuda.current_stream(dev).cuda_stream))
+    return pl[:num_rendered].to(torch.int64), rg.view(tiles, 2).to(torch.int64)

@@ -1,0 +1,208 @@
+/*
+ * gsicp_b200.h — C ABI of libgsicp_b200.so (sm_100a).
+ *
+ * Drop-in boundary for the two data-parallel hot paths of GS-ICP-SLAM
+ * (SURVEY.md §8b).  Every entry point cites the reference interface it
+ * replaces (paths relative to the reference checkout):
+ *
+ *   DGR = submodules/diff-gaussian-rasterization
+ *   FG  = submodules/fast_gicp
+ *   SK  = submodules/simple-knn
+ *
+ * Conventions: plain pointers and sizes only (no torch / Eigen / pybind types);
+ * all `const float*` / `float*` arguments named d_* are DEVICE pointers on the
+ * current CUDA device; `stream` is a cudaStream_t passed as void*; functions
+ * return >= 0 on success and a negative GSICP_E* code on failure (no exceptions
+ * cross the ABI); gsicp_last_error() returns a thread-local message.
+ */
+#ifndef GSICP_B200_H
+#define GSICP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GSICP_OK 0
+#define GSICP_EINVAL (-1)   /* bad argument (reference: AT_ERROR / std::invalid_argument) */
+#define GSICP_ECUDA (-2)    /* CUDA runtime error */
+#define GSICP_ENOMEM (-3)   /* workspace callback returned NULL */
+#define GSICP_ESTATE (-4)   /* call sequence error (e.g. align() without target) */
+
+const char* gsicp_last_error(void);
+/* "sm_100a" + build flags; lets host code verify the native library is the one loaded. */
+const char* gsicp_build_info(void);
+/* Number of kernel launches issued by this library since process start (bench.py: gpu_launches). */
+uint64_t gsicp_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Rasterizer (mapper hot path)
+ * ------------------------------------------------------------------------------------------ */
+
+/* Resizable-buffer callback: must return a device pointer to at least `bytes` bytes (128-B
+ * aligned) that stays valid until the matching backward call.  Mirrors the reference's
+ * std::function<char*(size_t)> resize functors (DGR/rasterize_points.cu:27-33). */
+typedef void* (*gsicp_alloc_fn)(size_t bytes, void* user);
+
+/* Inputs of one rasterization — the argument list of CudaRasterizer::Rasterizer::forward
+ * (DGR/cuda_rasterizer/rasterizer.h:35-60, rasterizer_impl.cu:201-227). */
+typedef struct gsicp_raster_args {
+  int P;                 /* number of Gaussians */
+  int D;                 /* active SH degree (0..3) */
+  int M;                 /* SH coefficients stored per Gaussian (0 if colours precomputed) */
+  int width, height;
+  float tan_fovx, tan_fovy;
+  float scale_modifier;
+  int prefiltered;       /* reference: trap if a "prefiltered" point is culled (auxiliary.h:161-165) */
+  int debug;             /* synchronise + check after every stage (auxiliary.h:171-178) */
+  const float* d_background;     /* [3] */
+  const float* d_means3D;        /* [P,3] */
+  const float* d_shs;            /* [P,M,3] or NULL */
+  const float* d_colors_precomp; /* [P,3]  or NULL */
+  const float* d_opacities;      /* [P] */
+  const float* d_scales;         /* [P,3] or NULL */
+  const float* d_rotations;      /* [P,4] (x,y,z,w), used UN-normalised (forward.cu:134-138) */
+  const float* d_cov3D_precomp;  /* [P,6] or NULL */
+  const float* d_viewmatrix;     /* [16] row-major storage of the transposed world->view */
+  const float* d_projmatrix;     /* [16] likewise, full projection */
+  const float* d_campos;         /* [3] */
+  /* Tile sharding for multi-GPU: this rank renders tiles t with
+   * t % tile_shard_count == tile_shard_index.  (1, 0) = all tiles. */
+  int tile_shard_count, tile_shard_index;
+} gsicp_raster_args;
+
+/* Forward.  Replaces RasterizeGaussiansCUDA -> Rasterizer::forward
+ * (DGR/rasterize_points.cu:35-121, rasterizer_impl.cu:201-347).
+ * Outputs (device, caller-allocated, zero-initialised like torch::full(...,0)):
+ *   d_out_color [3,H,W], d_out_depth [1,H,W], d_radii int32[P], d_is_used uint8[P].
+ * The three callbacks size the state kept for backward (private layout).
+ * Returns num_rendered (tile instances, >= 0) or a negative error. */
+int gsicp_raster_forward(const gsicp_raster_args* args,
+                         float* d_out_color, float* d_out_depth,
+                         int32_t* d_radii, uint8_t* d_is_used,
+                         gsicp_alloc_fn geom_alloc, gsicp_alloc_fn binning_alloc,
+                         gsicp_alloc_fn image_alloc, void* user, void* stream);
+
+/* Backward.  Replaces RasterizeGaussiansBackwardCUDA -> Rasterizer::backward
+ * (DGR/rasterize_points.cu:123-206, rasterizer_impl.cu:351-454).
+ * All gradient outputs are device buffers that the caller ZERO-fills
+ * (rasterize_points.cu:158-167): dL_dmeans2D[P,3], dL_dcolors[P,3], dL_dopacity[P],
+ * dL_dmeans3D[P,3], dL_dcov3D[P,6], dL_dsh[P,M,3], dL_dscales[P,3], dL_drotations[P,4].
+ * d_work must hold gsicp_raster_backward_work_bytes(P) zero-filled bytes (the reference's
+ * dL_dconic[P,6] + dL_ddepths[P] scratch). */
+size_t gsicp_raster_backward_work_bytes(int P);
+int gsicp_raster_backward(const gsicp_raster_args* args, int num_rendered,
+                          const int32_t* d_radii,
+                          const void* d_geom, const void* d_binning, const void* d_image,
+                          const float* d_dL_dout_color, const float* d_dL_dout_depth,
+                          float* d_dL_dmeans2D, float* d_dL_dcolors, float* d_dL_dopacity,
+                          float* d_dL_dmeans3D, float* d_dL_dcov3D, float* d_dL_dsh,
+                          float* d_dL_dscales, float* d_dL_drotations,
+                          void* d_work, void* stream);
+
+/* Introspection of the saved state for the parity tests (point_list bit-exactness):
+ * copies the sorted tile-instance list (uint32[num_rendered]) and the per-tile ranges
+ * (uint32[2*tiles]) out of the binning / image buffers.  Device -> device. */
+int gsicp_raster_export_binning(const gsicp_raster_args* args, int num_rendered,
+                                const void* d_binning, const void* d_image,
+                                uint32_t* d_point_list, uint32_t* d_ranges, void* stream);
+
+/* Replaces markVisible / checkFrustum (DGR/rasterize_points.cu:208-227,
+ * rasterizer_impl.cu:54-66): present[i] = view-space z > 0.2. */
+int gsicp_mark_visible(int P, const float* d_means3D, const float* d_viewmatrix,
+                       const float* d_projmatrix, uint8_t* d_present, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * simple-knn
+ * ------------------------------------------------------------------------------------------ */
+
+/* Replaces distCUDA2 -> SimpleKNN::knn (SK/spatial.cu:15-25, SK/simple_knn.cu:185-221):
+ * d_out[i] = mean of the 3 smallest squared distances from point i to the other points. */
+int gsicp_dist2(int P, const float* d_points, float* d_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * GICP tracker (pygicp.FastGICP).  Host pointers unless named d_*.
+ * ------------------------------------------------------------------------------------------ */
+
+typedef struct gsicp_gicp gsicp_gicp;
+
+/* FastGICP::FastGICP() defaults (FG/include/fast_gicp/gicp/impl/fast_gicp_impl.hpp:9-33,
+ * lsq_registration_impl.hpp:9-22): k=10, knn_max=0.5, NORMALIZED_ELLIPSE, LM, 64 iters. */
+gsicp_gicp* gsicp_gicp_create(void);
+void gsicp_gicp_destroy(gsicp_gicp*);
+
+int gsicp_gicp_set_max_correspondence_distance(gsicp_gicp*, double d);  /* main.cpp:204 */
+int gsicp_gicp_set_max_knn_distance(gsicp_gicp*, double d);             /* main.cpp:205, fgi:51-53 */
+int gsicp_gicp_set_correspondence_randomness(gsicp_gicp*, int k);       /* main.cpp:203 */
+int gsicp_gicp_set_max_iterations(gsicp_gicp*, int n);                  /* pcl::Registration::setMaximumIterations */
+
+/* set_input_source / set_input_target (main.cpp:167-168 + eigen2pcl :37-45, fgi:94-105,120-130):
+ * xyz is row-major (N,3) float64 on the host (is_f32 != 0: float32); stored as fp32; covariances
+ * and rotations/scales of that cloud are cleared; the NN grid over the cloud is rebuilt. */
+int gsicp_gicp_set_input_source(gsicp_gicp*, const void* xyz, int n, int is_f32);
+int gsicp_gicp_set_input_target(gsicp_gicp*, const void* xyz, int n, int is_f32);
+/* Zero-copy variants ("next" row N1): device fp32 (N,3). */
+int gsicp_gicp_set_input_source_device(gsicp_gicp*, const float* d_xyz, int n);
+int gsicp_gicp_set_input_target_device(gsicp_gicp*, const float* d_xyz, int n);
+
+/* set_source_filter / set_target_filter (main.cpp:254-261, fgi:189-202). */
+int gsicp_gicp_set_source_filter(gsicp_gicp*, int num_trackable, const int32_t* filter, int n);
+int gsicp_gicp_set_target_filter(gsicp_gicp*, int num_trackable, const int32_t* filter, int n);
+
+/* calculate_target_covariance_with_filter (fgi:157-166,710-825),
+ * calculate_source_covariance / calculate_target_covariance (fgi:107-117,132-142,382-479). */
+int gsicp_gicp_calculate_target_covariance_with_filter(gsicp_gicp*);
+int gsicp_gicp_calculate_source_covariance(gsicp_gicp*);
+int gsicp_gicp_calculate_target_covariance(gsicp_gicp*);
+
+/* set_source/target_covariances_fromqs (main.cpp:234-245, fgi:828-902). n = number of points. */
+int gsicp_gicp_set_source_covariances_fromqs(gsicp_gicp*, const float* rots_xyzw, const float* scales, int n);
+int gsicp_gicp_set_target_covariances_fromqs(gsicp_gicp*, const float* rots_xyzw, const float* scales, int n);
+
+/* align (main.cpp:173-179; pcl::Registration::align -> fgi:225-240 -> lsq:53-78).
+ * guess/out: row-major 4x4 float32.  Returns the number of LM outer iterations run. */
+int gsicp_gicp_align(gsicp_gicp*, const float guess[16], float out[16]);
+int gsicp_gicp_has_converged(gsicp_gicp*);
+int gsicp_gicp_get_final_hessian(gsicp_gicp*, double out[36]);          /* lsq:44-46 */
+
+/* Getters (main.cpp:206-233, fast_gicp.hpp:82-110). *_size return element counts. */
+int gsicp_gicp_source_size(gsicp_gicp*);          /* input_->size() (after filtering: trackable) */
+int gsicp_gicp_target_size(gsicp_gicp*);
+int gsicp_gicp_source_rotationsq_size(gsicp_gicp*);
+int gsicp_gicp_target_rotationsq_size(gsicp_gicp*);
+int gsicp_gicp_source_scales_size(gsicp_gicp*);
+int gsicp_gicp_target_scales_size(gsicp_gicp*);
+int gsicp_gicp_get_source_rotationsq(gsicp_gicp*, float* out);
+int gsicp_gicp_get_target_rotationsq(gsicp_gicp*, float* out);
+int gsicp_gicp_get_source_scales(gsicp_gicp*, float* out);
+int gsicp_gicp_get_target_scales(gsicp_gicp*, float* out);
+int gsicp_gicp_get_source_correspondence(gsicp_gicp*, int32_t* corr, float* sq_dist);
+/* Test/diagnostic access: regularised 3x3 covariances as 9 doubles per point (row-major). */
+int gsicp_gicp_get_source_covariances(gsicp_gicp*, double* out);
+int gsicp_gicp_get_target_covariances(gsicp_gicp*, double* out);
+
+/* One linearize at a given pose (LsqRegistration::evaluateCost, lsq:48-51): H row-major 6x6,
+ * b[6]; returns error through *err.  Used by the parity tests and by bench.py's roofline leg. */
+int gsicp_gicp_linearize(gsicp_gicp*, const double pose[16], double H[36], double b[6], double* err);
+int gsicp_gicp_compute_error(gsicp_gicp*, const double pose[16], double* err);
+
+/* Multi-GPU: shard the SOURCE points [shard_index::shard_count) and all-reduce the
+ * 28 doubles (21 H + 6 b + err) through the callback (torch.distributed / NCCL on the host side,
+ * or ncclAllReduce inside the library when comm != NULL).  reduce(user, d_buf28, stream). */
+typedef int (*gsicp_allreduce_fn)(void* user, double* d_buf, int count, void* stream);
+int gsicp_gicp_set_shard(gsicp_gicp*, int shard_count, int shard_index,
+                         gsicp_allreduce_fn reduce, void* user);
+
+/* Stream on which the handle's kernels run (default: legacy default stream 0). */
+int gsicp_gicp_set_stream(gsicp_gicp*, void* stream);
+/* Timing of the last align(): milliseconds spent in each stage, measured with CUDA events on the
+ * handle's stream: [0]=source covariance, [1]=linearize total, [2]=compute_error total,
+ * [3]=number of linearize launches, [4]=number of compute_error launches. */
+int gsicp_gicp_last_timing(gsicp_gicp*, double out[5]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GSICP_B200_H */
