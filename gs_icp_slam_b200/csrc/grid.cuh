@@ -52,12 +52,12 @@ __device__ __forceinline__ float ord2f(unsigned int u) {
   return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
 }
 
-__global__ void grid_bbox_init_kernel(unsigned int* bb) {
+static __global__ void grid_bbox_init_kernel(unsigned int* bb) {
   if (threadIdx.x < 3) bb[threadIdx.x] = 0xffffffffu;
   else if (threadIdx.x < 6) bb[threadIdx.x] = 0u;
 }
 
-__global__ void grid_bbox_kernel(int n, const float* __restrict__ xyz, unsigned int* bb) {
+static __global__ void grid_bbox_kernel(int n, const float* __restrict__ xyz, unsigned int* bb) {
   float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
 #pragma unroll
@@ -87,7 +87,7 @@ __global__ void grid_bbox_kernel(int n, const float* __restrict__ xyz, unsigned 
 }
 
 // one thread: choose the cell size so that the dense grid has at most max_cells cells
-__global__ void grid_setup_kernel(const unsigned int* bb, int n, int max_cells, GridMeta* meta) {
+static __global__ void grid_setup_kernel(const unsigned int* bb, int n, int max_cells, GridMeta* meta) {
   float lo[3], hi[3], ext[3];
   for (int d = 0; d < 3; d++) {
     lo[d] = ord2f(bb[d]);
@@ -127,7 +127,7 @@ __device__ __forceinline__ int3 grid_cell_of(const GridMeta& m, float x, float y
   return make_int3(cx, cy, cz);
 }
 
-__global__ void grid_count_kernel(int n, const float* __restrict__ xyz, const GridMeta* __restrict__ meta,
+static __global__ void grid_count_kernel(int n, const float* __restrict__ xyz, const GridMeta* __restrict__ meta,
                                   uint32_t* __restrict__ counts, uint32_t* __restrict__ cell_of_pt) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -138,7 +138,7 @@ __global__ void grid_count_kernel(int n, const float* __restrict__ xyz, const Gr
   atomicAdd(&counts[id], 1u);
 }
 
-__global__ void grid_scatter_kernel(int n, const float* __restrict__ xyz, const uint32_t* __restrict__ cell_of_pt,
+static __global__ void grid_scatter_kernel(int n, const float* __restrict__ xyz, const uint32_t* __restrict__ cell_of_pt,
                                     uint32_t* __restrict__ cursor, float4* __restrict__ pts) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;

@@ -1,0 +1,164 @@
+"""GPU parity of the rasterizer: our CUDA path (through the C ABI) vs
+  (1) the reference's own CUDA code compiled unmodified for sm_100a (oracle/_ref/libref_cuda.so), and
+  (2) the CPU restatement oracle/raster_oracle.c.
+Tolerances (BASELINE.json north_star): indices bit-exact; rendered L1 <= 1e-4, PSNR within 0.01 dB."""
+import numpy as np
+import pytest
+import torch
+
+from tests.util import psnr, rel_err, scene_tensors
+
+pytestmark = pytest.mark.gpu
+
+
+def _ours(t, c, H, W, bg, degree=0, colors=None, cov=None):
+    from gs_icp_slam_b200 import rasterizer as R
+
+    e = torch.Tensor([])
+    return R.rasterize_gaussians(bg, t["means3D"], e if colors is None else colors, t["opacities"],
+                                 e if cov is not None else t["scales"], e if cov is not None else t["rotations"], 1.0,
+                                 e if cov is None else cov, c["viewmatrix"], c["projmatrix"], c["tanfovx"], c["tanfovy"],
+                                 H, W, t["shs"] if colors is None else e, degree, c["campos"], False, False)
+
+
+def _ref(t, c, H, W, bg, degree=0):
+    from oracle import ref_cuda
+
+    if not ref_cuda.available():
+        pytest.skip("oracle/_ref/libref_cuda.so not built")
+    return ref_cuda.RefRaster(bg, t["means3D"], t["shs"], None, t["opacities"].reshape(-1), t["scales"], t["rotations"],
+                              None, c["viewmatrix"], c["projmatrix"], c["campos"], c["tanfovx"], c["tanfovy"], H, W, degree)
+
+
+@pytest.mark.parametrize("P,size,degree,seed", [(20000, (320, 240), 0, 2), (100000, (640, 480), 0, 3), (30000, (333, 211), 3, 5)])
+def test_forward_backward_vs_reference_cuda(cuda, P, size, degree, seed):
+    from gs_icp_slam_b200 import rasterizer as R
+
+    g, cm, t, c, cam = scene_tensors(P, seed, cuda, sh_degree=degree, size=size)
+    W, H = size
+    bg = torch.tensor([0.1, 0.2, 0.3], device=cuda)
+    n, depth, color, radii, is_used, geom, binning, img = _ours(t, c, H, W, bg, degree)
+    ref = _ref(t, c, H, W, bg, degree)
+
+    # ---- indexing: bit-exact ----
+    assert n == ref.num_rendered
+    assert torch.equal(radii, ref.radii)
+    assert torch.equal(is_used, ref.is_used)
+    pl, rg = R.export_binning(n, H, W, binning, img)
+    rpl, rrg = ref.export()
+    assert torch.equal(rg, rrg)
+    assert torch.equal(pl, rpl)
+
+    # ---- image: L1 / PSNR ----
+    col, rcol = color.cpu().numpy(), ref.color.cpu().numpy()
+    dep, rdep = depth.cpu().numpy(), ref.depth.cpu().numpy()
+    assert np.abs(col - rcol).mean() <= 1e-4
+    assert np.abs(col - rcol).max() <= 2e-3
+    assert np.abs(dep - rdep).mean() <= 1e-4
+    assert psnr(col, rcol) >= 80.0  # i.e. PSNR against any target differs by << 0.01 dB
+
+    # ---- gradients ----
+    gen = torch.Generator(device="cpu").manual_seed(seed + 5)
+    gcol = torch.randn((3, H, W), generator=gen).to(cuda)
+    gdep = torch.randn((1, H, W), generator=gen).to(cuda)
+    e = torch.Tensor([])
+    ours = R.rasterize_gaussians_backward(bg, t["means3D"], radii, e, t["scales"], t["rotations"], 1.0, e, c["viewmatrix"],
+                                          c["projmatrix"], c["tanfovx"], c["tanfovy"], gdep, gcol, t["shs"], degree,
+                                          c["campos"], geom, n, binning, img, False)
+    names = ["means2D", "colors", "opacity", "means3D", "cov3D", "sh", "scales", "rotations"]
+    rgrad = ref.backward(gcol, gdep)
+    for name, o in zip(names, ours):
+        r = rgrad[name]
+        if name == "colors":
+            continue  # the reference returns dL_dcolors only as an internal when SHs are used; compare below
+        err = rel_err(o.cpu().numpy(), r.cpu().numpy())
+        assert err <= 2e-4, f"grad {name}: rel err {err}"
+    assert rel_err(ours[1].cpu().numpy(), rgrad["colors"].cpu().numpy()) <= 2e-4
+    ref.free()
+
+
+def test_cull_is_exact(cuda):
+    """Sub-tile culling must not change a single bit of the output."""
+    from gs_icp_slam_b200 import _lib
+
+    g, cm, t, c, cam = scene_tensors(40000, 7, cuda, size=(320, 240))
+    bg = torch.zeros(3, device=cuda)
+    a = _ours(t, c, 240, 320, bg)
+    _lib.lib.gsicp_test_set_render_cull(0)
+    try:
+        b = _ours(t, c, 240, 320, bg)
+    finally:
+        _lib.lib.gsicp_test_set_render_cull(1)
+    assert a[0] == b[0]
+    assert torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])
+
+
+def test_vs_cpu_oracle(cuda):
+    from oracle import raster_oracle
+
+    P, (W, H) = 3000, (160, 120)
+    g, cm, t, c, cam = scene_tensors(P, 11, cuda, size=(W, H), sh_degree=1)
+    bgn = np.array([0.0, 0.5, 1.0], np.float32)
+    rng = np.random.default_rng(3)
+    gcol = rng.normal(size=(3, H, W)).astype(np.float32)
+    gdep = rng.normal(size=(1, H, W)).astype(np.float32)
+    o = raster_oracle.forward_backward(g, cm, H, W, bgn, sh_degree=1, dL_dcolor=gcol, dL_ddepth=gdep)
+    from gs_icp_slam_b200 import rasterizer as R
+
+    bg = torch.from_numpy(bgn).to(cuda)
+    n, depth, color, radii, is_used, geom, binning, img = _ours(t, c, H, W, bg, 1)
+    # CPU and GPU round differently (fma contraction), so indices may differ for Gaussians that sit exactly on a
+    # rounding boundary: demand exact equality here for this seed (it holds), and image closeness.
+    assert np.array_equal(radii.cpu().numpy(), o.radii)
+    assert n == o.num_rendered
+    assert np.abs(color.cpu().numpy() - o.color).mean() <= 1e-4
+    assert np.abs(depth.cpu().numpy() - o.depth).mean() <= 1e-4
+    e = torch.Tensor([])
+    ours = R.rasterize_gaussians_backward(bg, t["means3D"], radii, e, t["scales"], t["rotations"], 1.0, e, c["viewmatrix"],
+                                          c["projmatrix"], c["tanfovx"], c["tanfovy"], torch.from_numpy(gdep).to(cuda),
+                                          torch.from_numpy(gcol).to(cuda), t["shs"], 1, c["campos"], geom, n, binning, img,
+                                          False)
+    refs = [o.dL_dmeans2D, o.dL_dcolors, o.dL_dopacity, o.dL_dmeans3D, o.dL_dcov3D, o.dL_dsh, o.dL_dscales, o.dL_drotations]
+    for name, a, b in zip(["means2D", "colors", "opacity", "means3D", "cov3D", "sh", "scales", "rotations"], ours, refs):
+        assert rel_err(a.cpu().numpy().reshape(b.shape), b) <= 2e-4, name
+
+
+def test_autograd_api(cuda):
+    """The drop-in package: GaussianRasterizer(settings)(...) -> (depth, color, radii, is_used), backward fills grads."""
+    from diff_gaussian_rasterization import GaussianRasterizationSettings, GaussianRasterizer
+
+    g, cm, t, c, cam = scene_tensors(5000, 13, cuda, size=(160, 120))
+    for k in ("means3D", "shs", "opacities", "scales", "rotations"):
+        t[k].requires_grad_(True)
+    means2D = torch.zeros_like(t["means3D"], requires_grad=True)
+    rs = GaussianRasterizationSettings(120, 160, c["tanfovx"], c["tanfovy"], torch.zeros(3, device=cuda), 1.0,
+                                       c["viewmatrix"], c["projmatrix"], 0, c["campos"], False, False)
+    depth, color, radii, is_used = GaussianRasterizer(rs)(means3D=t["means3D"], means2D=means2D, opacities=t["opacities"],
+                                                          shs=t["shs"], scales=t["scales"], rotations=t["rotations"])
+    assert depth.shape == (1, 120, 160) and color.shape == (3, 120, 160)
+    assert radii.dtype == torch.int32 and is_used.dtype == torch.bool
+    (color.mean() + 0.1 * depth.mean()).backward()
+    for k in ("means3D", "shs", "opacities", "scales", "rotations"):
+        assert t[k].grad is not None and torch.isfinite(t[k].grad).all()
+    assert means2D.grad is not None and means2D.grad.abs().sum() > 0
+    with pytest.raises(Exception):
+        GaussianRasterizer(rs)(means3D=t["means3D"], means2D=means2D, opacities=t["opacities"])
+    vis = GaussianRasterizer(rs).markVisible(t["means3D"].detach())
+    assert vis.dtype == torch.bool and vis.shape[0] == 5000
+
+
+def test_empty_and_offscreen(cuda):
+    from gs_icp_slam_b200 import rasterizer as R
+
+    g, cm, t, c, cam = scene_tensors(100, 17, cuda, size=(64, 48))
+    bg = torch.tensor([0.3, 0.2, 0.1], device=cuda)
+    t0 = {k: v[:0] for k, v in t.items()}
+    out = _ours(t0, c, 48, 64, bg)
+    assert out[0] == 0 and out[2].abs().sum() == 0  # reference returns zero images when P == 0
+    # everything behind the camera: background only
+    t2 = dict(t)
+    t2["means3D"] = t["means3D"] * 0 + torch.from_numpy(cm["campos"]).to(cuda) - 5.0 * c["viewmatrix"][:3, 2]
+    out = _ours(t2, c, 48, 64, bg)
+    assert out[0] == 0
+    assert torch.allclose(out[2], bg.view(3, 1, 1).expand(3, 48, 64))
+    assert torch.allclose(out[1], torch.full((1, 48, 64), 15.0, device=cuda))
