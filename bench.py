@@ -1,0 +1,493 @@
+#!/usr/bin/env python
+"""bench.py — SLAM frames/s on the synthetic TUM-shape workload (BASELINE.json metric).
+
+One "step" = one SLAM frame of the two hot paths, in the order the reference's processes run them:
+  tracker  (mp_Tracker.py:191-231,256-288): set_input_source(12 416-pt cloud) -> set_source_filter -> align(prev pose)
+            -> get_source_correspondence; every 5th frame is a tracking keyframe: get_source_rotationsq/scales,
+            set_input_target(map points) + set_target_covariances_fromqs(map rotations, scales)
+  mapper   (mp_Mapper.py:219-242, one training iteration): GaussianRasterizer forward on the 300k-Gaussian map at the
+            frame's camera -> L1(colour) + 0.1 L1(depth) against the frame's RGB-D -> backward through the rasterizer
+            (loss arithmetic is a few PyTorch element-wise ops; Adam is outside the hot path).
+Workload = BASELINE config C3: 640x480, fx 517.3 ..., downsample 5, max_corr 0.03, 300 000 Gaussians (seed 3).
+
+Printed JSON (one line, rank 0): `value` = frames/s with every input already resident in HBM; `e2e.value` = frames/s
+through the public drop-in APIs with HOST inputs (numpy clouds / pinned images copied H2D inside the step, pose,
+correspondences and loss read back D2H); `roofline` = the kernel with the largest device time in the step, measured
+with CUDA events around its launches (gsicp_prof_*); `cpu_baseline` = the CPU oracle timed on the host cores.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+`--impl reference` = the reference's own implementation of the same frame on this box: the CPU GICP (oracle port of
+fast_gicp — PCL is absent so the original cannot be built) on all host cores + the reference's CUDA rasterizer
+compiled unmodified for sm_100a (oracle/_ref/libref_cuda.so).
+"""
+import argparse
+import json
+import math
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+KEYFRAME_EVERY = 5
+N_TRAJ = 200  # frames of the full synthetic trajectory; the bench walks its first W+K frames
+MAP_P = 300000
+MAP_SEED = 3
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--gaussians", type=int, default=MAP_P)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-roofline", action="store_true")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------
+# synthetic sequence
+# ----------------------------------------------------------------------------------------------
+def make_sequence(n_frames, P):
+    from gs_icp_slam_b200 import synthetic as S
+
+    cam = S.TUM
+    gmap = S.gaussian_map(P, MAP_SEED)
+    frames = []
+    for i in range(n_frames + 1):
+        c2w = S.trajectory_pose(i, N_TRAJ)
+        depth, hit = S.raycast_depth(c2w, cam)
+        rgb = S.texture(hit).astype(np.float32).reshape(cam["H"], cam["W"], 3).transpose(2, 0, 1).copy()
+        pts, tr = S.tracker_cloud(depth, cam)
+        frames.append(dict(c2w=c2w, depth=depth[None].copy(), rgb=rgb, pts=pts, filt=S.trackable_filter(len(pts), tr),
+                           n_trk=len(tr), cam=S.camera_matrices(c2w, cam)))
+    return cam, gmap, frames
+
+
+class ClockSampler:
+    """SM clock / throttle reasons during the timed region (pynvml; falls back to nvidia-smi)."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self.index = index
+        self.th = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        try:
+            import pynvml as nv
+
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
+                     "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                     "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                     "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+            while not self._stop.is_set():
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+                time.sleep(0.02)
+        except Exception as ex:  # no NVML in this environment
+            self.reasons.add(f"unavailable:{type(ex).__name__}")
+
+    def __enter__(self):
+        self.th.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self.th.join(timeout=2)
+
+    def summary(self):
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons)}
+
+
+# ----------------------------------------------------------------------------------------------
+# our implementation
+# ----------------------------------------------------------------------------------------------
+class Ours:
+    def __init__(self, cam, gmap, frames, dev, world, rank):
+        import torch
+
+        import pygicp
+        from diff_gaussian_rasterization import GaussianRasterizationSettings, GaussianRasterizer
+        from gs_icp_slam_b200 import _lib, rasterizer
+
+        self.torch, self.dev, self.cam, self.frames = torch, dev, cam, frames
+        self.world, self.rank = world, rank
+        self.Settings, self.Rasterizer, self._lib = GaussianRasterizationSettings, GaussianRasterizer, _lib
+        self.map_np = gmap
+        self.map = {k: torch.from_numpy(v).to(dev).requires_grad_(True) for k, v in gmap.items()}
+        self.means2D = torch.zeros_like(self.map["means3D"], requires_grad=True)
+        self.bg = torch.zeros(3, device=dev)
+        self.reg = pygicp.FastGICP()
+        self.reg.set_max_correspondence_distance(0.03)
+        self.reg.set_max_knn_distance(99999)
+        H, W = cam["H"], cam["W"]
+        # per-frame resident copies (value mode) and pinned host copies (e2e mode)
+        for f in frames:
+            f["d_pts"] = torch.from_numpy(f["pts"].astype(np.float32)).to(dev)
+            f["d_rgb"] = torch.from_numpy(f["rgb"]).to(dev)
+            f["d_depth"] = torch.from_numpy(f["depth"]).to(dev)
+            f["h_rgb"] = torch.from_numpy(f["rgb"]).pin_memory()
+            f["h_depth"] = torch.from_numpy(f["depth"]).pin_memory()
+            f["d_cam"] = {k: (torch.from_numpy(v).to(dev) if isinstance(v, np.ndarray) else v) for k, v in f["cam"].items()}
+        self.stage_rgb = torch.empty((3, H, W), device=dev)
+        self.stage_depth = torch.empty((1, H, W), device=dev)
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        self.pix_mask = None
+        if world > 1:
+            import torch.distributed as dist
+
+            self.dist = dist
+            rasterizer.set_tile_shard(world, rank)
+            ty, tx = (H + 15) // 16, (W + 15) // 16
+            tid = (torch.arange(ty, device=dev)[:, None] * tx + torch.arange(tx, device=dev)[None, :])
+            own = (tid % world == rank).repeat_interleave(16, 0).repeat_interleave(16, 1)[:H, :W]
+            self.pix_mask = own.float()[None]
+            self.reg.set_shard(world, rank, self._allreduce)
+        self.pose = frames[0]["c2w"].astype(np.float32)
+        self.stats = dict(R=0, V=0, n_src=0, n_corr=0, n_tgt=0, frames=0, h2d=0, d2h=0)
+        self.refresh_target(resident=True)
+
+    def _allreduce(self, ptr, count, stream):
+        torch = self.torch
+
+        class _Arr:
+            __cuda_array_interface__ = {"shape": (count,), "typestr": "<f8", "data": (ptr, False), "version": 3}
+
+        t = torch.as_tensor(_Arr(), device=self.dev)
+        self.dist.all_reduce(t)
+
+    def refresh_target(self, resident):
+        m = self.map
+        if resident:
+            self.reg.set_input_target(m["means3D"].detach())
+            self.reg.set_target_covariances_fromqs(m["rotations"].detach(), m["scales"].detach())
+        else:
+            g = self.map_np
+            self.reg.set_input_target(g["means3D"].astype(np.float64))
+            self.reg.set_target_covariances_fromqs(g["rotations"].reshape(-1), g["scales"].reshape(-1))
+            self.stats["h2d"] += g["means3D"].nbytes + g["rotations"].nbytes + g["scales"].nbytes
+
+    def step(self, i, resident):
+        torch = self.torch
+        f, prev = self.frames[i + 1], self.frames[i]
+        st = self.stats
+        # ---- tracker ----
+        if resident:
+            self.reg.set_input_source(f["d_pts"])
+        else:
+            self.reg.set_input_source(f["pts"])  # float64 numpy, as mp_Tracker hands it over
+            st["h2d"] += f["pts"].shape[0] * 12
+        self.reg.set_source_filter(f["n_trk"], f["filt"])
+        st["h2d"] += f["filt"].nbytes
+        pose = self.reg.align(prev["c2w"].astype(np.float32))
+        corr, sqd = self.reg.get_source_correspondence()
+        st["d2h"] += 64 + corr.nbytes + sqd.nbytes
+        st["n_src"] += len(corr)
+        st["n_corr"] += int((corr >= 0).sum())
+        st["n_tgt"] += self.map["means3D"].shape[0]
+        st["n_lin"] = st.get("n_lin", 0) + self.reg.last_iterations
+        self.pose = pose
+        if (i + 1) % KEYFRAME_EVERY == 0:
+            rots, scales = self.reg.get_source_rotationsq(), self.reg.get_source_scales()
+            st["d2h"] += rots.nbytes + scales.nbytes
+            self.refresh_target(resident)
+        # ---- mapper: one training iteration ----
+        if resident:
+            gt_rgb, gt_depth = f["d_rgb"], f["d_depth"]
+        else:
+            self.stage_rgb.copy_(f["h_rgb"], non_blocking=True)
+            self.stage_depth.copy_(f["h_depth"], non_blocking=True)
+            gt_rgb, gt_depth = self.stage_rgb, self.stage_depth
+            st["h2d"] += f["h_rgb"].numel() * 4 + f["h_depth"].numel() * 4
+        c, cam, m = f["d_cam"], self.cam, self.map
+        rs = self.Settings(cam["H"], cam["W"], c["tanfovx"], c["tanfovy"], self.bg, 1.0, c["viewmatrix"], c["projmatrix"], 0,
+                           c["campos"], False, False)
+        depth, color, radii, is_used = self.Rasterizer(rs)(means3D=m["means3D"], means2D=self.means2D,
+                                                           opacities=m["opacities"], shs=m["shs"], scales=m["scales"],
+                                                           rotations=m["rotations"])
+        if self.pix_mask is None:
+            loss = (color - gt_rgb).abs().mean() + 0.1 * (depth - gt_depth).abs().mean()
+        else:
+            n = float(gt_depth.numel())
+            loss = ((color - gt_rgb).abs() * self.pix_mask).sum() / (3 * n) + 0.1 * ((depth - gt_depth).abs() * self.pix_mask).sum() / n
+        loss.backward()
+        if self.world > 1:
+            flat = torch.cat([m[k].grad.reshape(-1) for k in ("means3D", "shs", "opacities", "scales", "rotations")])
+            self.dist.all_reduce(flat)
+        lv = float(loss.item())  # D2H read of the step's result
+        st["d2h"] += 8
+        for k in m:
+            m[k].grad = None
+        self.means2D.grad = None
+        st["R"] += getattr(color.grad_fn, "num_rendered", 0) if color.grad_fn is not None else 0
+        st["V"] += int((radii > 0).sum())
+        st["frames"] += 1
+        return lv
+
+    def run(self, steps, warmup, resident, profile=False):
+        torch = self.torch
+        self._lib.prof_enable(False)
+        for k in self.stats:
+            self.stats[k] = 0
+        self.refresh_target(resident=True)
+        times = []
+        for i in range(warmup + steps):
+            if i == warmup:
+                for k in self.stats:
+                    self.stats[k] = 0
+                if self.world > 1:
+                    self.dist.barrier()
+                torch.cuda.synchronize()
+                self._lib.prof_reset()
+                self._lib.prof_enable(profile)
+                self.launch0 = self._lib.launch_count()
+            self.flush.fill_(i & 0xff)  # L2 flush between steps (outside the timed events)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            self.step(i, resident)
+            e1.record()
+            torch.cuda.synchronize()
+            if i >= warmup:
+                times.append(e0.elapsed_time(e1))
+        if self.world > 1:
+            self.dist.barrier()
+        torch.cuda.synchronize()
+        self._lib.prof_enable(False)
+        launches = self._lib.launch_count() - self.launch0
+        return float(np.sum(times)), launches, dict(self.stats)
+
+
+# ----------------------------------------------------------------------------------------------
+# reference arm / CPU baseline
+# ----------------------------------------------------------------------------------------------
+def cpu_frame(reg, gmap, frames, i, raster):
+    """One frame on the CPU oracle: GICP align (all cores) + (optionally) the raster oracle fwd+bwd (1 core)."""
+    from oracle import raster_oracle
+
+    f, prev = frames[i + 1], frames[i]
+    reg.set_input_source(f["pts"])
+    reg.set_source_filter(f["n_trk"], f["filt"])
+    reg.align(prev["c2w"].astype(np.float32))
+    reg.get_source_correspondence()
+    if (i + 1) % KEYFRAME_EVERY == 0:
+        reg.get_source_rotationsq()
+        reg.get_source_scales()
+        reg.set_input_target(gmap["means3D"].astype(np.float64))
+        reg.set_target_covariances_fromqs(gmap["rotations"].reshape(-1), gmap["scales"].reshape(-1))
+    if raster:
+        H, W = f["rgb"].shape[1:]
+        o = raster_oracle.forward_backward(gmap, f["cam"], H, W, np.zeros(3, np.float32))
+        gc = np.sign(o.color - f["rgb"]).astype(np.float32) / o.color.size
+        gd = 0.1 * np.sign(o.depth - f["depth"]).astype(np.float32) / o.depth.size
+        raster_oracle.forward_backward(gmap, f["cam"], H, W, np.zeros(3, np.float32), dL_dcolor=gc, dL_ddepth=gd)
+
+
+def cpu_baseline(gmap, frames, budget_s=20.0):
+    from oracle import gicp_oracle as G
+
+    reg = G.FastGICP()
+    reg.set_max_correspondence_distance(0.03)
+    reg.set_max_knn_distance(99999)
+    reg.set_input_target(gmap["means3D"].astype(np.float64))
+    reg.set_target_covariances_fromqs(gmap["rotations"].reshape(-1), gmap["scales"].reshape(-1))
+    t0, n = time.time(), 0
+    while n < min(3, len(frames) - 1) and (time.time() - t0 < budget_s or n == 0):
+        cpu_frame(reg, gmap, frames, n, raster=True)
+        n += 1
+    dt = time.time() - t0
+    return {"value": n / dt, "unit": "frames/s", "cores": G.num_threads(), "kind": "port",
+            "sample": f"{n} frame(s): oracle GICP align on {G.num_threads()} threads + raster oracle fwd+bwd on 1 thread, "
+                      f"640x480, {gmap['means3D'].shape[0]} Gaussians"}
+
+
+def reference_arm(args, cam, gmap, frames):
+    """Reference implementation of the frame on this box: CPU GICP oracle + reference CUDA rasterizer (if a GPU and
+    oracle/_ref/libref_cuda.so are present; the CPU raster oracle otherwise)."""
+    from oracle import gicp_oracle as G
+    from oracle import ref_cuda
+
+    use_gpu = False
+    try:
+        import torch
+
+        use_gpu = torch.cuda.is_available() and ref_cuda.available()
+    except Exception:
+        pass
+    reg = G.FastGICP()
+    reg.set_max_correspondence_distance(0.03)
+    reg.set_max_knn_distance(99999)
+    reg.set_input_target(gmap["means3D"].astype(np.float64))
+    reg.set_target_covariances_fromqs(gmap["rotations"].reshape(-1), gmap["scales"].reshape(-1))
+    if use_gpu:
+        dev = torch.device("cuda:0")
+        m = {k: torch.from_numpy(v).to(dev) for k, v in gmap.items()}
+        bg = torch.zeros(3, device=dev)
+        for f in frames:
+            f["d_rgb"], f["d_depth"] = torch.from_numpy(f["rgb"]).to(dev), torch.from_numpy(f["depth"]).to(dev)
+            f["d_cam"] = {k: (torch.from_numpy(v).to(dev) if isinstance(v, np.ndarray) else v) for k, v in f["cam"].items()}
+
+    def step(i):
+        f = frames[i + 1]
+        cpu_frame(reg, gmap, frames, i, raster=not use_gpu)
+        if use_gpu:
+            c = f["d_cam"]
+            r = ref_cuda.RefRaster(bg, m["means3D"], m["shs"], None, m["opacities"].reshape(-1), m["scales"], m["rotations"],
+                                   None, c["viewmatrix"], c["projmatrix"], c["campos"], c["tanfovx"], c["tanfovy"],
+                                   cam["H"], cam["W"], 0)
+            gc = torch.sign(r.color - f["d_rgb"]) / r.color.numel()
+            gd = 0.1 * torch.sign(r.depth - f["d_depth"]) / r.depth.numel()
+            r.backward(gc, gd)
+            torch.cuda.synchronize()
+            r.free()
+
+    for i in range(args.warmup):
+        step(i)
+    t0 = time.time()
+    for i in range(args.warmup, args.warmup + args.steps):
+        step(i)
+    dt = time.time() - t0
+    fps = args.steps / dt
+    mapper = "reference CUDA rasterizer (oracle/_ref, sm_100a) on cuda:0" if use_gpu else "CPU raster oracle (1 thread)"
+    return {"metric": "SLAM frames/sec (synthetic 640x480 RGB-D, 300k Gaussians)", "value": fps, "unit": "frames/s",
+            "impl": "reference", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64 (GICP) / f32 (rasterizer)", "data": "synthetic",
+            "config": workload_config(args, mapper=mapper),
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": G.num_threads(), "kind": "port",
+                             "sample": f"{args.steps} frames: oracle GICP (fast_gicp restatement, PCL absent) + {mapper}"},
+            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+
+
+def workload_config(args, **extra):
+    c = {"workload": f"C3 TUM-shape: 640x480 RGB-D, {args.gaussians} Gaussians (seed {MAP_SEED}), 12416 source points/frame, "
+                     f"max_corr 0.03, keyframe every {KEYFRAME_EVERY} (target refresh), 1 mapper iteration (raster fwd + "
+                     "L1 colour/depth loss + raster bwd) per frame",
+         "l2": "256 MiB write between steps, excluded from the per-step CUDA-event time",
+         "parallelism": "single GPU" if args.gpus == 1 else f"tile-sharded rasterizer + point-sharded GICP over {args.gpus} GPUs (NCCL all-reduce)"}
+    c.update(extra)
+    return c
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", 0))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    n_frames = args.warmup + args.steps
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        cam, gmap, frames = make_sequence(n_frames, args.gaussians)
+        print(json.dumps(reference_arm(args, cam, gmap, frames)))
+        return
+
+    import torch
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — gs_icp_slam_b200 has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+    cam, gmap, frames = make_sequence(n_frames, args.gaussians)
+    eng = Ours(cam, gmap, frames, dev, world, rank)
+    from gs_icp_slam_b200 import _lib
+
+    with ClockSampler(local_rank) as clk:
+        t_res, launches, st_res = eng.run(args.steps, args.warmup, resident=True)
+        t_e2e, _, st_e2e = eng.run(args.steps, args.warmup, resident=False)
+    clocks = clk.summary()
+    prof = {}
+    if not args.no_roofline:
+        _, _, st_p = eng.run(args.steps, args.warmup, resident=True, profile=True)
+        prof = _lib.prof_read()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    t_res, t_e2e = max_over_ranks(t_res), max_over_ranks(t_e2e)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    K = args.steps
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback (B200_PROFILING.md)")
+
+    roofline, kernels = None, {}
+    if prof:
+        tiles = ((cam["W"] + 15) // 16) * ((cam["H"] + 15) // 16)
+        npix = cam["W"] * cam["H"]
+        R, V = st_p["R"] / K, st_p["V"] / K
+        n_src, n_corr, n_tgt = st_p["n_src"] / K, st_p["n_corr"] / K, st_p["n_tgt"] / K
+        alg = {  # algorithmic bytes per launch (SURVEY.md §8d / DESIGN.md §5)
+            "render_forward": 8 * tiles + 52 * R + 36 * npix,
+            "render_backward": 8 * tiles + 52 * R + 36 * npix + 56 * V,
+            "gicp_linearize": 60 * n_src + 60 * n_corr + 12 * n_tgt + 224,
+            "gicp_error": 12 * n_src + 60 * n_corr + 8,
+            "preprocess": 56 * args.gaussians + 5 * args.gaussians + 79 * V,
+            "gaussian_backward": V * 139 + args.gaussians * 64,
+            "tile_sort": 12 * R * 2 * 2,
+            "depth_sort": 8 * args.gaussians * 2 * 4 + 8 * args.gaussians,
+            "gicp_covariance": 160 * n_src + 60 * n_src,
+        }
+        for name, (ms, n) in prof.items():
+            if n > 0:
+                per = ms / n
+                kernels[name] = {"launches_per_step": n / K, "ms_per_launch": per, "ms_per_step": ms / K}
+                if name in alg:
+                    kernels[name]["achieved_GBps"] = alg[name] / (per * 1e-3) / 1e9
+        top = max((k for k in kernels if k in alg), key=lambda k: kernels[k]["ms_per_step"])
+        ach = kernels[top]["achieved_GBps"]
+        roofline = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                    "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg[top],
+                    "ms_per_launch": kernels[top]["ms_per_launch"],
+                    "render_fwd_bwd_GBps": (alg["render_forward"] + alg["render_backward"]) / 1e9 /
+                    ((kernels["render_forward"]["ms_per_launch"] + kernels["render_backward"]["ms_per_launch"]) * 1e-3)
+                    if "render_forward" in kernels and "render_backward" in kernels else None}
+
+    out = {"metric": "SLAM frames/sec (synthetic 640x480 RGB-D, 300k Gaussians)", "value": K / (t_res * 1e-3),
+           "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": args.warmup, "ms_per_step": t_res / K,
+           "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+           "dtype": "f64 (GICP algebra on f32 points) / f32 (rasterizer)", "data": "synthetic",
+           "config": workload_config(args, lm_iterations_per_frame=st_res.get("n_lin", 0) / K,
+                                     tile_instances_per_frame=st_res["R"] / K, visible_gaussians_per_frame=st_res["V"] / K),
+           "clocks": clocks, "gpu_launches": launches,
+           "e2e": {"value": K / (t_e2e * 1e-3), "unit": "frames/s", "ms_per_step": t_e2e / K,
+                   "h2d_bytes_per_step": st_e2e["h2d"] / K, "d2h_bytes_per_step": st_e2e["d2h"] / K},
+           "roofline": roofline, "kernels": kernels}
+    if world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(gmap, frames)
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -69,6 +69,12 @@ _sig("gsicp_last_error", C.c_char_p, [])
 _sig("gsicp_build_info", C.c_char_p, [])
 _sig("gsicp_launch_count", C.c_uint64, [])
 
+_sig("gsicp_prof_enable", None, [i32])
+_sig("gsicp_prof_reset", None, [])
+_sig("gsicp_prof_count", i32, [])
+_sig("gsicp_prof_name", C.c_char_p, [i32])
+_sig("gsicp_prof_read", i32, [i32, f64p, C.POINTER(C.c_long)])
+
 _sig("gsicp_raster_forward", i32, [C.POINTER(RasterArgs), vp, vp, vp, vp, ALLOC_FN, ALLOC_FN, ALLOC_FN, vp, vp])
 _sig("gsicp_raster_backward_work_bytes", C.c_size_t, [i32])
 _sig("gsicp_raster_backward", i32, [C.POINTER(RasterArgs), i32, vp, vp, vp, vp, vp, vp] + [vp] * 8 + [vp, vp])
@@ -88,6 +94,7 @@ for _n in ("source", "target"):
     _sig(f"gsicp_gicp_set_input_{_n}_device", i32, [vp, vp, i32])
     _sig(f"gsicp_gicp_set_{_n}_filter", i32, [vp, i32, vp, i32])
     _sig(f"gsicp_gicp_set_{_n}_covariances_fromqs", i32, [vp, vp, vp, i32])
+    _sig(f"gsicp_gicp_set_{_n}_covariances_fromqs_device", i32, [vp, vp, vp, i32])
     _sig(f"gsicp_gicp_{_n}_size", i32, [vp])
     _sig(f"gsicp_gicp_{_n}_rotationsq_size", i32, [vp])
     _sig(f"gsicp_gicp_{_n}_scales_size", i32, [vp])
@@ -132,3 +139,21 @@ def build_info():
 
 def launch_count():
     return int(lib.gsicp_launch_count())
+
+
+def prof_enable(on=True):
+    lib.gsicp_prof_enable(1 if on else 0)
+
+
+def prof_reset():
+    lib.gsicp_prof_reset()
+
+
+def prof_read():
+    """{kernel name: (total_ms, launches)} accumulated since the last reset (device time, CUDA events)."""
+    out = {}
+    for k in range(lib.gsicp_prof_count()):
+        ms, n = C.c_double(0), C.c_long(0)
+        lib.gsicp_prof_read(k, C.byref(ms), C.byref(n))
+        out[lib.gsicp_prof_name(k).decode()] = (ms.value, n.value)
+    return out

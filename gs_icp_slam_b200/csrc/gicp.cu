@@ -564,6 +564,7 @@ int set_cloud(gsicp_gicp* h, Cloud& c, const void* xyz, int n, int is_f32, bool 
     for (size_t i = 0; i < cnt; i++) out[i] = (float)in[i];
     GSICP_CUDA(cudaMemcpyAsync(c.xyz.ptr, h->h_stage, cnt * sizeof(float), cudaMemcpyHostToDevice, h->stream));
   }
+  ProfScope ps(kProfGridBuild, h->stream);
   return c.grid.build(c.xyz.as<float>(), n, h->stream);
 }
 
@@ -618,9 +619,12 @@ int compute_covariances(gsicp_gicp* h, Cloud& c, bool with_filter, bool clamp) {
   a.filter = d_filter; a.xyz = c.xyz.as<float>(); a.rots = c.rots.as<float>(); a.scales = c.scales.as<float>();
   a.cov = c.cov.as<double>(); a.new_xyz = with_filter ? c.xyz_alt.as<float>() : nullptr;
   const int grid = (n + 127) / 128;
+  {
+  ProfScope ps(kProfCovariance, h->stream);
   if (h->k <= 10) GSICP_LAUNCH(covariance_kernel<10>, grid, 128, 0, h->stream, c.grid.view(), a);
   else if (h->k <= 20) GSICP_LAUNCH(covariance_kernel<20>, grid, 128, 0, h->stream, c.grid.view(), a);
   else GSICP_LAUNCH(covariance_kernel<32>, grid, 128, 0, h->stream, c.grid.view(), a);
+  }
   GSICP_CUDA(cudaGetLastError());
   c.rots_n = 4 * n;
   c.scales_n = 3 * n;
@@ -634,12 +638,18 @@ int compute_covariances(gsicp_gicp* h, Cloud& c, bool with_filter, bool clamp) {
   return GSICP_OK;
 }
 
-int covs_from_qs(gsicp_gicp* h, Cloud& c, const float* rots, const float* scales, int n) {
+int covs_from_qs(gsicp_gicp* h, Cloud& c, const float* rots, const float* scales, int n, bool device_src = false) {
   if (n < 0 || (n > 0 && (!rots || !scales))) return GSICP_EINVAL;
   if (int e = c.cov.ensure((size_t)(n > 0 ? n : 1) * 6 * sizeof(double))) return e;
   if (int e = c.rots.ensure((size_t)(n > 0 ? n : 1) * 4 * sizeof(float))) return e;
   if (int e = c.scales.ensure((size_t)(n > 0 ? n : 1) * 3 * sizeof(float))) return e;
-  if (n > 0) {
+  if (n > 0 && device_src) {
+    GSICP_CUDA(cudaMemcpyAsync(c.rots.ptr, rots, (size_t)n * 4 * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
+    GSICP_CUDA(cudaMemcpyAsync(c.scales.ptr, scales, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
+    GSICP_LAUNCH(cov_from_qs_kernel, (n + 255) / 256, 256, 0, h->stream, n, c.rots.as<float>(), c.scales.as<float>(),
+                 c.cov.as<double>());
+    GSICP_CUDA(cudaGetLastError());
+  } else if (n > 0) {
     if (int e = ensure_stage(h, (size_t)n * 7 * sizeof(float))) return e;
     GSICP_CUDA(cudaStreamSynchronize(h->stream));
     float* st = (float*)h->h_stage;
@@ -706,7 +716,8 @@ int run_linearize(gsicp_gicp* h, const Iso& x, double H[6][6], double b[6], doub
   a.partial = h->partial.as<double>(); a.out = h->red_out.as<double>(); a.counter = h->counter.as<unsigned int>();
   int blocks = (end - begin + kLinBlock - 1) / kLinBlock;
   if (blocks < 1) blocks = 1;
-  GSICP_LAUNCH(linearize_kernel, blocks, kLinBlock, 0, h->stream, h->tgt.grid.view(), make_pose(x), a);
+  { ProfScope ps(kProfLinearize, h->stream);
+  GSICP_LAUNCH(linearize_kernel, blocks, kLinBlock, 0, h->stream, h->tgt.grid.view(), make_pose(x), a); }
   if (h->shard_count > 1 && h->reduce) {
     const int rc = h->reduce(h->reduce_user, h->red_out.as<double>(), kRed, (void*)h->stream);
     if (rc != 0) {
@@ -744,7 +755,8 @@ int run_error(gsicp_gicp* h, const Iso& x, double* err) {  // fgi:355-378
   a.partial = h->partial.as<double>(); a.out = h->red_out.as<double>(); a.counter = h->counter.as<unsigned int>();
   int blocks = (end - begin + kLinBlock - 1) / kLinBlock;
   if (blocks < 1) blocks = 1;
-  GSICP_LAUNCH(error_kernel, blocks, kLinBlock, 0, h->stream, make_pose(x), a);
+  { ProfScope ps(kProfError, h->stream);
+  GSICP_LAUNCH(error_kernel, blocks, kLinBlock, 0, h->stream, make_pose(x), a); }
   if (h->shard_count > 1 && h->reduce) {
     const int rc = h->reduce(h->reduce_user, h->red_out.as<double>(), 1, (void*)h->stream);
     if (rc != 0) return GSICP_ECUDA;
@@ -901,6 +913,8 @@ int gsicp_gicp_calculate_target_covariance(gsicp_gicp* h) { H_CHECK(h); return c
 
 int gsicp_gicp_set_source_covariances_fromqs(gsicp_gicp* h, const float* r, const float* s, int n) { H_CHECK(h); return covs_from_qs(h, h->src, r, s, n); }
 int gsicp_gicp_set_target_covariances_fromqs(gsicp_gicp* h, const float* r, const float* s, int n) { H_CHECK(h); return covs_from_qs(h, h->tgt, r, s, n); }
+int gsicp_gicp_set_source_covariances_fromqs_device(gsicp_gicp* h, const float* r, const float* s, int n) { H_CHECK(h); return covs_from_qs(h, h->src, r, s, n, true); }
+int gsicp_gicp_set_target_covariances_fromqs_device(gsicp_gicp* h, const float* r, const float* s, int n) { H_CHECK(h); return covs_from_qs(h, h->tgt, r, s, n, true); }
 
 int gsicp_gicp_align(gsicp_gicp* h, const float guess[16], float out[16]) {
   H_CHECK(h);

@@ -28,6 +28,21 @@ void set_error(const char* fmt, ...);
     }                                                                                     \
   } while (0)
 
+// Optional per-kernel device timing (bench.py roofline leg): when enabled, the hot kernels are bracketed by
+// CUDA events recorded on the launching stream; totals are resolved when read.  Off by default.
+enum ProfKernel {
+  kProfPreprocess = 0, kProfDepthSort, kProfEmit, kProfTileSort, kProfRenderFwd, kProfRenderBwd, kProfGaussBwd,
+  kProfCovariance, kProfLinearize, kProfError, kProfGridBuild, kProfDist2, kProfCount
+};
+extern bool g_prof_on;
+void prof_begin(int k, cudaStream_t s);
+void prof_end(int k, cudaStream_t s);
+struct ProfScope {
+  int k; cudaStream_t s;
+  ProfScope(int kk, cudaStream_t ss) : k(kk), s(ss) { if (g_prof_on) prof_begin(k, s); }
+  ~ProfScope() { if (g_prof_on) prof_end(k, s); }
+};
+
 // Grow-only device scratch buffer (library-internal workspace that backward does not need).
 struct Scratch {
   void* ptr = nullptr;

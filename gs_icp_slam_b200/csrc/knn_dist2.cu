@@ -33,6 +33,7 @@ extern "C" int gsicp_dist2(int P, const float* d_points, float* d_out, void* str
   if (P == 0) return GSICP_OK;
   cudaStream_t stream = (cudaStream_t)stream_v;
   std::lock_guard<std::mutex> lock(g_dist2_mu);
+  ProfScope ps(kProfDist2, stream);
   if (int e = g_dist2_grid.build(d_points, P, stream)) return e;
   GSICP_LAUNCH(dist2_kernel, (P + 127) / 128, 128, 0, stream, g_dist2_grid.view(), d_points, d_out);
   GSICP_CUDA(cudaGetLastError());

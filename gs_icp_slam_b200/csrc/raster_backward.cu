@@ -493,6 +493,7 @@ extern "C" int gsicp_raster_backward(const gsicp_raster_args* args, int num_rend
   float* work = (float*)d_work;
 
   if (num_rendered > 0) {
+    ProfScope ps(kProfRenderBwd, stream);
     if (g_render_cull) {
       GSICP_LAUNCH(render_backward_kernel<true>, tiles, kTilePixels, 0, stream, img.ranges, bin.point_list, W, H, tiles_x,
                    args->d_background, geom.splats, img.final_T, img.n_contrib, d_dL_dout_color, d_dL_dout_depth,
@@ -514,6 +515,7 @@ extern "C" int gsicp_raster_backward(const gsicp_raster_args* args, int num_rend
   ba.means = args->d_means3D; ba.scales = args->d_scales; ba.rots = args->d_rotations;
   ba.shs = args->d_shs; ba.cov_pre = args->d_cov3D_precomp; ba.view = args->d_viewmatrix; ba.proj = args->d_projmatrix;
   ba.campos = args->d_campos;
+  ProfScope ps_gb(kProfGaussBwd, stream);
   GSICP_LAUNCH(gaussian_backward_kernel, (P + 255) / 256, 256, 0, stream, ba, d_radii, geom.clamped, work, d_dL_dmeans2D,
                d_dL_dcolors, d_dL_dmeans3D, d_dL_dcov3D, d_dL_dsh, d_dL_dscales, d_dL_drotations);
   if (args->debug) GSICP_CUDA(cudaStreamSynchronize(stream));

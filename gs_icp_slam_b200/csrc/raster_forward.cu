@@ -409,8 +409,11 @@ extern "C" int gsicp_raster_forward(const gsicp_raster_args* args, float* d_out_
     pa.view = args->d_viewmatrix; pa.proj = args->d_projmatrix; pa.campos = args->d_campos;
     pa.prefiltered = args->prefiltered; pa.shard_count = shard_count; pa.shard_index = shard_index;
     const int grid = (P + 255) / 256;
-    GSICP_LAUNCH(preprocess_kernel, grid, 256, 0, stream, pa, d_radii, d_is_used, geom.splats, geom.clamped, depth_key,
-                 ident, tiles_touched);
+    {
+      ProfScope ps(kProfPreprocess, stream);
+      GSICP_LAUNCH(preprocess_kernel, grid, 256, 0, stream, pa, d_radii, d_is_used, geom.splats, geom.clamped, depth_key,
+                   ident, tiles_touched);
+    }
     if (args->debug) GSICP_CUDA(cudaStreamSynchronize(stream));
 
     // depth sort (31 significant bits: positive floats and the invisible sentinel)
@@ -419,12 +422,14 @@ extern "C" int gsicp_raster_forward(const gsicp_raster_args* args, float* d_out_
     cub::DeviceScan::InclusiveSum(nullptr, tmp2, counts, offsets, P, stream);
     if (int e = g_fwd.cub_tmp.ensure(tmp1 > tmp2 ? tmp1 : tmp2)) return e;
     size_t tmp = g_fwd.cub_tmp.cap;
+    ProfScope* ps_sort = new ProfScope(kProfDepthSort, stream);
     GSICP_CUDA(cub::DeviceRadixSort::SortPairs(g_fwd.cub_tmp.ptr, tmp, depth_key, depth_sorted, ident, order, P, 0, 31,
                                                stream));
     g_launches.fetch_add(4, std::memory_order_relaxed);
     GSICP_LAUNCH(gather_counts_kernel, grid, 256, 0, stream, P, order, tiles_touched, counts);
     tmp = g_fwd.cub_tmp.cap;
     GSICP_CUDA(cub::DeviceScan::InclusiveSum(g_fwd.cub_tmp.ptr, tmp, counts, offsets, P, stream));
+    delete ps_sort;
     g_launches.fetch_add(1, std::memory_order_relaxed);
 
     // The Python API returns num_rendered as a host int (DGR/diff_gaussian_rasterization/__init__.py:96),
@@ -460,8 +465,10 @@ extern "C" int gsicp_raster_forward(const gsicp_raster_args* args, float* d_out_
     const int bits = (int)bits_for((uint32_t)tiles);
     size_t tmp = 0;
     if (k16) {
+      { ProfScope ps(kProfEmit, stream);
       GSICP_LAUNCH(emit_instances_kernel<uint16_t>, gridP, 256, 0, stream, P, order, offsets, tiles_touched, geom.splats,
-                   d_radii, tiles_x, tiles_y, shard_count, shard_index, (uint16_t*)keys_in, vals_in);
+                   d_radii, tiles_x, tiles_y, shard_count, shard_index, (uint16_t*)keys_in, vals_in); }
+      ProfScope ps_ts(kProfTileSort, stream);
       cub::DeviceRadixSort::SortPairs(nullptr, tmp, (uint16_t*)keys_in, (uint16_t*)keys_out, vals_in, bin.point_list, R, 0,
                                       bits, stream);
       if (int e = g_fwd.cub_tmp.ensure(tmp)) return e;
@@ -470,8 +477,10 @@ extern "C" int gsicp_raster_forward(const gsicp_raster_args* args, float* d_out_
                                                  bin.point_list, R, 0, bits, stream));
       GSICP_LAUNCH(tile_ranges_kernel<uint16_t>, gridR, 256, 0, stream, R, (const uint16_t*)keys_out, img.ranges);
     } else {
+      { ProfScope ps(kProfEmit, stream);
       GSICP_LAUNCH(emit_instances_kernel<uint32_t>, gridP, 256, 0, stream, P, order, offsets, tiles_touched, geom.splats,
-                   d_radii, tiles_x, tiles_y, shard_count, shard_index, (uint32_t*)keys_in, vals_in);
+                   d_radii, tiles_x, tiles_y, shard_count, shard_index, (uint32_t*)keys_in, vals_in); }
+      ProfScope ps_ts(kProfTileSort, stream);
       cub::DeviceRadixSort::SortPairs(nullptr, tmp, (uint32_t*)keys_in, (uint32_t*)keys_out, vals_in, bin.point_list, R, 0,
                                       bits, stream);
       if (int e = g_fwd.cub_tmp.ensure(tmp)) return e;
@@ -485,6 +494,7 @@ extern "C" int gsicp_raster_forward(const gsicp_raster_args* args, float* d_out_
   }
 
   if (P > 0) {
+    ProfScope ps(kProfRenderFwd, stream);
     if (g_render_cull) {
       GSICP_LAUNCH(render_forward_kernel<true>, tiles, kTilePixels, 0, stream, img.ranges, bin.point_list, W, H, tiles_x,
                    geom.splats, args->d_background, d_out_color, d_out_depth, img.final_T, img.n_contrib, shard_count,

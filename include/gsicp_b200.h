@@ -37,6 +37,14 @@ const char* gsicp_build_info(void);
 /* Number of kernel launches issued by this library since process start (bench.py: gpu_launches). */
 uint64_t gsicp_launch_count(void);
 
+/* Per-kernel device timing for the roofline leg of bench.py: when enabled, the hot kernels are bracketed by
+ * CUDA events on their launching stream.  Kernels are indexed 0..gsicp_prof_count()-1 (gsicp_prof_name). */
+void gsicp_prof_enable(int on);
+void gsicp_prof_reset(void);
+int gsicp_prof_count(void);
+const char* gsicp_prof_name(int k);
+int gsicp_prof_read(int k, double* total_ms, long* count);
+
 /* ------------------------------------------------------------------------------------------
  * Rasterizer (mapper hot path)
  * ------------------------------------------------------------------------------------------ */
@@ -160,6 +168,9 @@ int gsicp_gicp_calculate_target_covariance(gsicp_gicp*);
 /* set_source/target_covariances_fromqs (main.cpp:234-245, fgi:828-902). n = number of points. */
 int gsicp_gicp_set_source_covariances_fromqs(gsicp_gicp*, const float* rots_xyzw, const float* scales, int n);
 int gsicp_gicp_set_target_covariances_fromqs(gsicp_gicp*, const float* rots_xyzw, const float* scales, int n);
+/* Zero-copy variants ("next" row N3): device fp32 arrays. */
+int gsicp_gicp_set_source_covariances_fromqs_device(gsicp_gicp*, const float* d_rots_xyzw, const float* d_scales, int n);
+int gsicp_gicp_set_target_covariances_fromqs_device(gsicp_gicp*, const float* d_rots_xyzw, const float* d_scales, int n);
 
 /* align (main.cpp:173-179; pcl::Registration::align -> fgi:225-240 -> lsq:53-78).
  * guess/out: row-major 4x4 float32.  Returns the number of LM outer iterations run. */
