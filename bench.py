@@ -150,25 +150,15 @@ class Ours:
         if world > 1:
             import torch.distributed as dist
 
-            self.dist = dist
+            from gs_icp_slam_b200 import sharding
+
+            self.dist, self.sharding = dist, sharding
             rasterizer.set_tile_shard(world, rank)
-            ty, tx = (H + 15) // 16, (W + 15) // 16
-            tid = (torch.arange(ty, device=dev)[:, None] * tx + torch.arange(tx, device=dev)[None, :])
-            own = (tid % world == rank).repeat_interleave(16, 0).repeat_interleave(16, 1)[:H, :W]
-            self.pix_mask = own.float()[None]
-            self.reg.set_shard(world, rank, self._allreduce)
+            self.pix_mask = sharding.tile_owner_mask(H, W, world, rank, dev)
+            self.reg.set_shard(world, rank, sharding.make_gicp_allreduce(dev))
         self.pose = frames[0]["c2w"].astype(np.float32)
         self.stats = dict(R=0, V=0, n_src=0, n_corr=0, n_tgt=0, frames=0, h2d=0, d2h=0)
         self.refresh_target(resident=True)
-
-    def _allreduce(self, ptr, count, stream):
-        torch = self.torch
-
-        class _Arr:
-            __cuda_array_interface__ = {"shape": (count,), "typestr": "<f8", "data": (ptr, False), "version": 3}
-
-        t = torch.as_tensor(_Arr(), device=self.dev)
-        self.dist.all_reduce(t)
 
     def refresh_target(self, resident):
         m = self.map
@@ -222,12 +212,11 @@ class Ours:
         if self.pix_mask is None:
             loss = (color - gt_rgb).abs().mean() + 0.1 * (depth - gt_depth).abs().mean()
         else:
-            n = float(gt_depth.numel())
-            loss = ((color - gt_rgb).abs() * self.pix_mask).sum() / (3 * n) + 0.1 * ((depth - gt_depth).abs() * self.pix_mask).sum() / n
+            sh = self.sharding
+            loss = sh.sharded_l1(color, gt_rgb, self.pix_mask, gt_rgb.numel()) + 0.1 * sh.sharded_l1(depth, gt_depth, self.pix_mask, gt_depth.numel())
         loss.backward()
         if self.world > 1:
-            flat = torch.cat([m[k].grad.reshape(-1) for k in ("means3D", "shs", "opacities", "scales", "rotations")])
-            self.dist.all_reduce(flat)
+            self.sharding.allreduce_grads([m[k] for k in ("means3D", "shs", "opacities", "scales", "rotations")])
         lv = float(loss.item())  # D2H read of the step's result
         st["d2h"] += 8
         for k in m:

@@ -49,15 +49,45 @@ struct CovArgs {
   float* new_xyz;    // [3 * num_trackable] (only with filter)
 };
 
+constexpr int kKnnGroup = 4;  // lanes cooperating on one k-NN query
+
+// k-NN of every point of the cloud in itself: ids and squared distances, sorted by (d2, id)
 template <int K>
-__global__ void __launch_bounds__(128)
-covariance_kernel(GridView g, CovArgs a) {
+__global__ void __launch_bounds__(128, 2)
+knn_kernel(GridView g, int n, int k, const float* __restrict__ xyz, uint32_t* __restrict__ nn_id, float* __restrict__ nn_d2) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = tid / kKnnGroup, gl = tid % kKnnGroup;
+  if (i >= n) return;  // group-uniform
+  const unsigned gmask = ((1u << kKnnGroup) - 1u) << ((threadIdx.x & 31) & ~(kKnnGroup - 1));
+  TopK<K> nn;
+  const int kk = min(k, K);
+  // the query point itself is its own nearest neighbour (distance 0), as with the reference's kd-tree search
+  grid_knn<K, kKnnGroup>(g, xyz[3 * (size_t)i], xyz[3 * (size_t)i + 1], xyz[3 * (size_t)i + 2], kk, 0xffffffffu, nn, gl, gmask);
+  grid_knn_merge<K, kKnnGroup>(nn, kk, gmask);
+  if (gl == 0) {
+#pragma unroll
+    for (int j = 0; j < K; j++) {
+      if (j < kk) {
+        nn_id[(size_t)i * K + j] = nn.id[j];
+        nn_d2[(size_t)i * K + j] = nn.d2[j];
+      }
+    }
+  }
+}
+
+template <int K>
+__global__ void __launch_bounds__(128, 1)
+covariance_kernel(CovArgs a, const uint32_t* __restrict__ nn_id, const float* __restrict__ nn_d2) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= a.n) return;
   const float qx = a.xyz[3 * (size_t)i], qy = a.xyz[3 * (size_t)i + 1], qz = a.xyz[3 * (size_t)i + 2];
-  TopK<K> nn;
   const int kk = min(a.k, K);
-  grid_knn<K>(g, qx, qy, qz, kk, 0xffffffffu, nn);  // the query point itself is its own nearest neighbour
+  struct { uint32_t id[K]; float d2[K]; } nn;
+#pragma unroll
+  for (int j = 0; j < K; j++) {
+    nn.id[j] = (j < kk) ? nn_id[(size_t)i * K + j] : 0xffffffffu;
+    nn.d2[j] = (j < kk) ? nn_d2[(size_t)i * K + j] : FLT_MAX;
+  }
 
   const int found = min(kk, a.n);
   int reliable = 0;  // neighbours are sorted ascending, so the reliable ones are a prefix
@@ -222,9 +252,13 @@ struct LinArgs {
   unsigned int* counter;
 };
 
-__global__ void __launch_bounds__(kLinBlock)
+constexpr int kLinGroup = 4;  // lanes cooperating on one source point's nearest-neighbour search
+
+__global__ void __launch_bounds__(kLinBlock, 1)
 linearize_kernel(GridView tgt, PoseD T, LinArgs a) {
-  const int i = a.begin + blockIdx.x * blockDim.x + threadIdx.x;
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = a.begin + tid / kLinGroup, gl = tid % kLinGroup;
+  const unsigned gmask = ((1u << kLinGroup) - 1u) << ((threadIdx.x & 31) & ~(kLinGroup - 1));
   double v[kRed];
 #pragma unroll
   for (int k = 0; k < kRed; k++) v[k] = 0.0;
@@ -236,13 +270,16 @@ linearize_kernel(GridView tgt, PoseD T, LinArgs a) {
     const float ty = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(T.Rf[1][0], px), __fmul_rn(T.Rf[1][1], py)), __fmul_rn(T.Rf[1][2], pz)), T.tf[1]);
     const float tz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(T.Rf[2][0], px), __fmul_rn(T.Rf[2][1], py)), __fmul_rn(T.Rf[2][2], pz)), T.tf[2]);
     TopK<1> nn;
-    grid_knn<1>(tgt, tx, ty, tz, 1, 0xffffffffu, nn);
+    grid_knn<1, kLinGroup>(tgt, tx, ty, tz, 1, 0xffffffffu, nn, gl, gmask);
+    grid_knn_merge<1, kLinGroup>(nn, 1, gmask);
     const float d2 = nn.d2[0];
-    a.sqd[i] = d2;
     const bool matched = (tgt.n > 0) && ((double)d2 < a.max_corr_sq);
     const int32_t j = matched ? (int32_t)nn.id[0] : -1;
-    a.corr[i] = j;
-    if (matched) {
+    if (gl == 0) {
+      a.sqd[i] = d2;
+      a.corr[i] = j;
+    }
+    if (matched && gl == 0) {
       const double* ca = a.src_cov + 6 * (size_t)i;
       const double* cb = a.tgt_cov + 6 * (size_t)j;
       const double A[3][3] = {{ca[0], ca[1], ca[2]}, {ca[1], ca[3], ca[4]}, {ca[2], ca[4], ca[5]}};
@@ -494,7 +531,7 @@ struct gsicp_gicp {
   float final_transformation[16];
   double final_hessian[36];
   cudaStream_t stream = 0;
-  Scratch corr, sqd, mahal, partial, red_out, counter, staging_dev;
+  Scratch corr, sqd, mahal, partial, red_out, counter, staging_dev, nn_id, nn_d2;
   int corr_n = 0;
   double* h_red = nullptr;     // pinned [28]
   void* h_stage = nullptr;     // pinned staging for H2D conversions
@@ -621,9 +658,22 @@ int compute_covariances(gsicp_gicp* h, Cloud& c, bool with_filter, bool clamp) {
   const int grid = (n + 127) / 128;
   {
   ProfScope ps(kProfCovariance, h->stream);
-  if (h->k <= 10) GSICP_LAUNCH(covariance_kernel<10>, grid, 128, 0, h->stream, c.grid.view(), a);
-  else if (h->k <= 20) GSICP_LAUNCH(covariance_kernel<20>, grid, 128, 0, h->stream, c.grid.view(), a);
-  else GSICP_LAUNCH(covariance_kernel<32>, grid, 128, 0, h->stream, c.grid.view(), a);
+  const int K = h->k <= 10 ? 10 : (h->k <= 20 ? 20 : 32);
+  if (int e = h->nn_id.ensure((size_t)n * K * 4)) return e;
+  if (int e = h->nn_d2.ensure((size_t)n * K * 4)) return e;
+  uint32_t* nid = h->nn_id.as<uint32_t>();
+  float* nd2 = h->nn_d2.as<float>();
+  const int kgrid = (int)(((size_t)n * kKnnGroup + 127) / 128);
+  if (K == 10) {
+    GSICP_LAUNCH(knn_kernel<10>, kgrid, 128, 0, h->stream, c.grid.view(), n, h->k, c.xyz.as<float>(), nid, nd2);
+    GSICP_LAUNCH(covariance_kernel<10>, grid, 128, 0, h->stream, a, nid, nd2);
+  } else if (K == 20) {
+    GSICP_LAUNCH(knn_kernel<20>, kgrid, 128, 0, h->stream, c.grid.view(), n, h->k, c.xyz.as<float>(), nid, nd2);
+    GSICP_LAUNCH(covariance_kernel<20>, grid, 128, 0, h->stream, a, nid, nd2);
+  } else {
+    GSICP_LAUNCH(knn_kernel<32>, kgrid, 128, 0, h->stream, c.grid.view(), n, h->k, c.xyz.as<float>(), nid, nd2);
+    GSICP_LAUNCH(covariance_kernel<32>, grid, 128, 0, h->stream, a, nid, nd2);
+  }
   }
   GSICP_CUDA(cudaGetLastError());
   c.rots_n = 4 * n;
@@ -681,7 +731,7 @@ void shard_range(const gsicp_gicp* h, int n, int& begin, int& end) {
 
 int ensure_lin_buffers(gsicp_gicp* h) {
   const int n = h->src.n;
-  const int blocks = (n + kLinBlock - 1) / kLinBlock + 1;
+  const int blocks = (int)(((size_t)n * kLinGroup + kLinBlock - 1) / kLinBlock) + 1;
   if (int e = h->corr.ensure((size_t)(n + 1) * 4)) return e;
   if (int e = h->sqd.ensure((size_t)(n + 1) * 4)) return e;
   if (int e = h->mahal.ensure((size_t)(n + 1) * 6 * sizeof(double))) return e;
@@ -714,7 +764,7 @@ int run_linearize(gsicp_gicp* h, const Iso& x, double H[6][6], double b[6], doub
   a.tgt_xyz = h->tgt.xyz.as<float>(); a.tgt_cov = h->tgt.cov.as<double>();
   a.corr = h->corr.as<int32_t>(); a.sqd = h->sqd.as<float>(); a.mahal = h->mahal.as<double>();
   a.partial = h->partial.as<double>(); a.out = h->red_out.as<double>(); a.counter = h->counter.as<unsigned int>();
-  int blocks = (end - begin + kLinBlock - 1) / kLinBlock;
+  int blocks = (int)(((size_t)(end - begin) * kLinGroup + kLinBlock - 1) / kLinBlock);
   if (blocks < 1) blocks = 1;
   { ProfScope ps(kProfLinearize, h->stream);
   GSICP_LAUNCH(linearize_kernel, blocks, kLinBlock, 0, h->stream, h->tgt.grid.view(), make_pose(x), a); }
@@ -869,7 +919,7 @@ void gsicp_gicp_destroy(gsicp_gicp* h) {
     fr(c->grid.meta_buf); fr(c->grid.bbox_buf); fr(c->grid.cell_start); fr(c->grid.cursor); fr(c->grid.cell_of_pt);
     fr(c->grid.pts); fr(c->grid.cub_tmp);
   }
-  fr(h->corr); fr(h->sqd); fr(h->mahal); fr(h->partial); fr(h->red_out); fr(h->counter); fr(h->staging_dev);
+  fr(h->corr); fr(h->sqd); fr(h->mahal); fr(h->partial); fr(h->red_out); fr(h->counter); fr(h->staging_dev); fr(h->nn_id); fr(h->nn_d2);
   if (h->h_red) cudaFreeHost(h->h_red);
   if (h->h_stage) cudaFreeHost(h->h_stage);
   if (h->ev0) cudaEventDestroy(h->ev0);

@@ -231,44 +231,53 @@ struct TopK {
   }
 };
 
-// Exact k-nearest search of (qx,qy,qz) in the grid.  kth = number of neighbours that must be final
-// (<= K).  exclude = original index to skip (0xffffffff: none).
-template <int K>
-__device__ __forceinline__ void grid_knn(const GridView& g, float qx, float qy, float qz, int kth, uint32_t exclude,
-                                         TopK<K>& best) {
+// Exact k-nearest search of (qx,qy,qz) in the grid by a GROUP of G consecutive lanes (G = 1, 2, 4, 8 ...).
+//   kth     = number of neighbours that must be final (<= K);  exclude = original index to skip (0xffffffff: none)
+//   g       = lane's rank inside its group, gmask = shuffle mask of the group's lanes (all must call together)
+// The cells of ring r form (2r+1)^2 x-rows; the points of consecutive x cells are contiguous in `pts`, so a shell row is
+// ONE contiguous point range (two cell_start loads).  Rows are dealt round-robin to the lanes of the group, each lane keeps
+// its own sorted top-K, and the ring loop stops when the group has seen `want` candidates closer than the nearest
+// unsearched cell face — the same exact criterion as a single sorted list (a lane's list truncates only when it alone
+// holds K >= want such candidates).  Call grid_knn_merge afterwards to obtain the group's sorted top-kth in every lane.
+template <int K, int G>
+__device__ __forceinline__ void grid_knn(const GridView& g_, float qx, float qy, float qz, int kth, uint32_t exclude,
+                                         TopK<K>& best, int g = 0, unsigned gmask = 0xffffffffu) {
   best.init();
-  if (g.n <= 0) return;
-  const GridMeta m = *g.meta;
+  if (g_.n <= 0) return;
+  const GridMeta m = *g_.meta;
   const int3 c0 = grid_cell_of(m, qx, qy, qz);
-  const int want = min(kth, g.n - (exclude != 0xffffffffu ? 1 : 0));
-  bool finished = false;
-  for (int r = 0; r <= kMaxRing; r++) {
+  const int want = min(kth, g_.n - (exclude != 0xffffffffu ? 1 : 0));
+  bool finished = (want <= 0);
+  auto scan_range = [&](uint32_t b, uint32_t e) {
+    for (uint32_t i = b; i < e; i++) {
+      const float4 p = g_.pts[i];
+      const uint32_t pid = __float_as_uint(p.w);
+      if (pid == exclude) continue;
+      best.push(dist2_nofma(p.x, p.y, p.z, qx, qy, qz), pid);
+    }
+  };
+  for (int r = 0; r <= kMaxRing && !finished; r++) {
     const int x0 = max(c0.x - r, 0), x1 = min(c0.x + r, m.nx - 1);
     const int y0 = max(c0.y - r, 0), y1 = min(c0.y + r, m.ny - 1);
     const int z0 = max(c0.z - r, 0), z1 = min(c0.z + r, m.nz - 1);
-    auto visit = [&](int x, int y, int z) {
-      const int cell = (z * m.ny + y) * m.nx + x;
-      const uint32_t b = g.cell_start[cell], e = g.cell_start[cell + 1];
-      for (uint32_t i = b; i < e; i++) {
-        const float4 p = g.pts[i];
-        const uint32_t pid = __float_as_uint(p.w);
-        if (pid == exclude) continue;
-        best.push(dist2_nofma(p.x, p.y, p.z, qx, qy, qz), pid);
-      }
-    };
+    int row = 0;
     for (int z = z0; z <= z1; z++) {
-      for (int y = y0; y <= y1; y++) {
-        if (abs(z - c0.z) == r || abs(y - c0.y) == r) {  // row lies on the shell: every x
-          for (int x = x0; x <= x1; x++) visit(x, y, z);
+      for (int y = y0; y <= y1; y++, row++) {
+        if (G > 1 && (row % G) != g) continue;
+        const int base = (z * m.ny + y) * m.nx;
+        if (abs(z - c0.z) == r || abs(y - c0.y) == r) {  // row lies on the shell: cells x0..x1 are one point range
+          scan_range(g_.cell_start[base + x0], g_.cell_start[base + x1 + 1]);
         } else {  // interior row: only the two end cells belong to ring r
-          if (c0.x - r >= 0) visit(c0.x - r, y, z);
-          if (c0.x + r <= m.nx - 1) visit(c0.x + r, y, z);
+          if (c0.x - r >= 0) scan_range(g_.cell_start[base + c0.x - r], g_.cell_start[base + c0.x - r + 1]);
+          if (c0.x + r <= m.nx - 1) scan_range(g_.cell_start[base + c0.x + r], g_.cell_start[base + c0.x + r + 1]);
         }
       }
     }
-    // squared distance below which no unsearched point can exist
-    const bool all = (x0 == 0 && y0 == 0 && z0 == 0 && x1 == m.nx - 1 && y1 == m.ny - 1 && z1 == m.nz - 1);
-    if (all) { finished = true; break; }
+    if (x0 == 0 && y0 == 0 && z0 == 0 && x1 == m.nx - 1 && y1 == m.ny - 1 && z1 == m.nz - 1) {
+      finished = true;  // the whole grid has been searched
+      break;
+    }
+    // distance below which no unsearched point can exist: nearest face of the searched cube that has cells beyond it
     float bound = FLT_MAX;
     if (c0.x - r > 0) bound = fminf(bound, qx - (m.ox + (c0.x - r) * m.cell));
     if (c0.x + r < m.nx - 1) bound = fminf(bound, (m.ox + (c0.x + r + 1) * m.cell) - qx);
@@ -276,21 +285,64 @@ __device__ __forceinline__ void grid_knn(const GridView& g, float qx, float qy, 
     if (c0.y + r < m.ny - 1) bound = fminf(bound, (m.oy + (c0.y + r + 1) * m.cell) - qy);
     if (c0.z - r > 0) bound = fminf(bound, qz - (m.oz + (c0.z - r) * m.cell));
     if (c0.z + r < m.nz - 1) bound = fminf(bound, (m.oz + (c0.z + r + 1) * m.cell) - qz);
-    bound = fmaxf(bound, 0.f);
-    // conservative: shrink the bound by the fp32 error of the face coordinates and of the distances
-    const float safe = bound * (1.0f - 1e-5f) - 1e-6f * m.cell;
-    if (want > 0 && safe > 0.f && best.d2[want - 1] < safe * safe * (1.0f - 1e-5f)) { finished = true; break; }
-    if (want <= 0) { finished = true; break; }
+    // conservative: shrink by the fp32 error of the face coordinates and of the distances
+    const float safe = fmaxf(bound, 0.f) * (1.0f - 1e-5f) - 1e-6f * m.cell;
+    if (safe > 0.f) {
+      const float lim = safe * safe * (1.0f - 1e-5f);
+      int cnt = 0;
+#pragma unroll
+      for (int i = 0; i < K; i++) cnt += (best.d2[i] < lim) ? 1 : 0;
+#pragma unroll
+      for (int o = 1; o < G; o <<= 1) cnt += __shfl_xor_sync(gmask, cnt, o);
+      if (cnt >= want) finished = true;
+    }
   }
-  if (!finished) {  // far outside the occupied cells: exact linear scan
+  if (!finished) {  // far outside the occupied cells: exact linear scan, interleaved over the group
     best.init();
-    for (int i = 0; i < g.n; i++) {
-      const float4 p = g.pts[i];
+    for (int i = g; i < g_.n; i += G) {
+      const float4 p = g_.pts[i];
       const uint32_t pid = __float_as_uint(p.w);
       if (pid == exclude) continue;
       best.push(dist2_nofma(p.x, p.y, p.z, qx, qy, qz), pid);
     }
   }
+}
+
+// Merge the G per-lane lists of a group: afterwards every lane of the group holds the group's sorted top-`kth`
+// (entries beyond kth are unspecified).  G = 1: no-op.
+template <int K, int G>
+__device__ __forceinline__ void grid_knn_merge(TopK<K>& best, int kth, unsigned gmask) {
+  if (G == 1) return;
+  TopK<K> out;
+  out.init();
+#pragma unroll
+  for (int t = 0; t < K; t++) {
+    if (t < kth) {
+      float wd = best.d2[0];
+      uint32_t wi = best.id[0];
+#pragma unroll
+      for (int o = 1; o < G; o <<= 1) {
+        const float od = __shfl_xor_sync(gmask, wd, o);
+        const uint32_t oi = __shfl_xor_sync(gmask, wi, o);
+        if (od < wd || (od == wd && oi < wi)) {
+          wd = od;
+          wi = oi;
+        }
+      }
+      out.d2[t] = wd;
+      out.id[t] = wi;
+      if (best.id[0] == wi && best.d2[0] == wd && wi != 0xffffffffu) {  // this lane owned the winner: pop it
+#pragma unroll
+        for (int i = 0; i < K - 1; i++) {
+          best.d2[i] = best.d2[i + 1];
+          best.id[i] = best.id[i + 1];
+        }
+        best.d2[K - 1] = FLT_MAX;
+        best.id[K - 1] = 0xffffffffu;
+      }
+    }
+  }
+  best = out;
 }
 
 }  // namespace gsicp

@@ -25,22 +25,9 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-__device__ __forceinline__ bool subtile_hit_bw(const float4 a, const float4 b, float wx0, float wy0) {
-  const float A = a.z, B = a.w, C = b.x, o = b.y;
-  const float det = A * C - B * B;
-  const float t255 = 255.f * o;
-  if (!(t255 >= 0.999f)) return false;
-  if (!(A > 0.f && C > 0.f && det > 0.f)) return true;
-  const float tau = fmaxf(__logf(t255), 0.f) * 1.001f + 2e-3f;
-  const float inv = 2.f * tau / det;
-  const float hx = sqrtf(inv * C) * 1.0005f + 1e-3f;
-  const float hy = sqrtf(inv * A) * 1.0005f + 1e-3f;
-  return (a.x + hx >= wx0) && (a.x - hx <= wx0 + 7.f) && (a.y + hy >= wy0) && (a.y - hy <= wy0 + 3.f);
-}
-
 // work[P][8] = { dconic_xx, dconic_xy, dconic_yy, dcov_zx, dcov_yz, ddepth, -, - }
 template <bool kCull>
-__global__ void __launch_bounds__(kTilePixels)
+__global__ void __launch_bounds__(kTilePixels, 3)
 render_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H,
                        int tiles_x, const float* __restrict__ bg, const Splat* __restrict__ splats,
                        const float* __restrict__ final_T, const uint32_t* __restrict__ n_contrib,
@@ -87,6 +74,10 @@ render_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restr
   float last_alpha = 0.f, last_r = 0.f, last_g = 0.f, last_b = 0.f, last_depth = 0.f;
   float acc_r = 0.f, acc_g = 0.f, acc_b = 0.f, acc_d = 0.f;
   const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
+  // lane roles of the recursive-halving reduction (see below)
+  const bool b16 = lane & 16, b8 = lane & 8, b4 = lane & 4, b2 = lane & 2;
+  const int red_var = (b16 ? 6 : 0) + (b8 ? 3 : 0) + (b4 ? 2 : (b2 ? 1 : 0));
+  const bool red_valid = !(b4 && b2) && !(lane & 1);
 
   // Back to front: batch `base` covers list positions [total-base-n, total-base), staged reversed
   // (sX[k] = position total-base-1-k) like backward.cu:519-531.
@@ -115,7 +106,7 @@ render_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restr
         {
           const int j = c0 + lane;
           bool hit = (j < n) && (first_pos - j <= warp_last);
-          if (kCull) hit = hit && subtile_hit_bw(sA[j < n ? j : 0], sB[j < n ? j : 0], (float)wx0, (float)wy0);
+          if (kCull) hit = hit && subtile_hit(sA[j < n ? j : 0], sB[j < n ? j : 0], (float)wx0, (float)wy0, 7.f, 3.f);
           mask = __ballot_sync(0xffffffffu, hit);
         }
         while (mask) {
@@ -129,6 +120,9 @@ render_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restr
           const float G = expf(power);
           const float alpha = fminf(0.99f, b.y * G);
           const bool active = inside && (contributor <= last_contributor) && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
+
+          const unsigned act = __ballot_sync(0xffffffffu, active);
+          if (!act) continue;  // no pixel of this sub-tile blended the instance: skip the gradient arithmetic
 
           float g[kG];
 #pragma unroll
@@ -179,14 +173,35 @@ render_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restr
             g[10] = dpd * d_covyz;
             g[11] = G * dL_dalpha + G * dL_dalpha_d;
           }
-          if (__any_sync(0xffffffffu, active)) {
+          {
+            if (__popc(act) <= 2) {
+              // one or two pixels of the sub-tile see this Gaussian (ellipse edge): add them directly
+              if (active) {
 #pragma unroll
-            for (int k = 0; k < kG; k++) g[k] = warp_sum(g[k]);
-            if (lane == 0) {
+                for (int k = 0; k < kG; k++) atomicAdd(&sAcc[k * kTilePixels + j], g[k]);
+              }
+            } else {
+              // Recursive-halving reduction: at each step a lane keeps half of its running sums and hands the other
+              // half to its partner, so the 12 sums over 32 lanes cost 6+3+2+1+1 = 13 shuffles (a butterfly per
+              // value would cost 60).  Sum k ends up in lane red_lane_of(k) (and its xor-1 neighbour).
+              float h[6], q[3];
 #pragma unroll
-              for (int k = 0; k < kG; k++) atomicAdd(&sAcc[k * kTilePixels + j], g[k]);
-              atomicOr(&sTouched[j >> 5], 1u << (j & 31));
+              for (int i = 0; i < 6; i++) {
+                const float send = b16 ? g[i] : g[i + 6], keep = b16 ? g[i + 6] : g[i];
+                h[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+              }
+#pragma unroll
+              for (int i = 0; i < 3; i++) {
+                const float send = b8 ? h[i] : h[i + 3], keep = b8 ? h[i + 3] : h[i];
+                q[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+              }
+              const float r0 = (b4 ? q[2] : q[0]) + __shfl_xor_sync(0xffffffffu, b4 ? q[0] : q[2], 4);
+              const float r1 = (b4 ? 0.f : q[1]) + __shfl_xor_sync(0xffffffffu, b4 ? q[1] : 0.f, 4);
+              float sum = (b2 ? r1 : r0) + __shfl_xor_sync(0xffffffffu, b2 ? r0 : r1, 2);
+              sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+              if (red_valid) atomicAdd(&sAcc[red_var * kTilePixels + j], sum);
             }
+            if (lane == 0) atomicOr(&sTouched[j >> 5], 1u << (j & 31));
           }
         }
       }

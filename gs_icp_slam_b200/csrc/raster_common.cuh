@@ -155,6 +155,39 @@ __device__ __forceinline__ void tile_rect(float px, float py, int radius, int ti
   y1 = min(tiles_y, max(0, (int)((py + radius + kTile - 1) / kTile)));
 }
 
+// Sub-tile culling shared by the forward and backward render kernels.
+// A tile instance contributes to pixel p iff power(p) = -q(p - c) <= 0 and opacity * exp(power) >= 1/255, i.e.
+// q(p - c) <= tau := ln(255 * opacity), with q(d) = 0.5 (A dx^2 + C dy^2) + B dx dy (the conic).  The warp's pixels lie
+// in the rectangle [x0, x0+w] x [y0, y0+h]; q is convex, so its minimum over the rectangle is 0 if the centre is
+// inside, else it is attained on the edge(s) facing the centre, where q restricted to the edge is a 1-D quadratic
+// whose minimiser is clamped to the edge.  The instance is culled iff that exact minimum exceeds tau (plus a safety
+// margin for fp32 rounding) — exactly the instances the reference skips for every pixel of the rectangle
+// (forward.cu:359-366), so the blend is unchanged bit for bit.
+__device__ __forceinline__ bool subtile_hit(const float4 a, const float4 b, float x0, float y0, float w, float h) {
+  const float A = a.z, B = a.w, C = b.x, o = b.y;
+  const float t255 = 255.f * o;
+  if (!(t255 >= 0.999f)) return false;  // alpha = o * exp(power <= 0) can never reach 1/255
+  if (!(A > 0.f && C > 0.f && A * C - B * B > 0.f)) return true;  // not an ellipse: do not cull
+  const float tau = fmaxf(__logf(t255), 0.f) * 1.0005f + 2e-3f;
+  const float cx = a.x, cy = a.y, x1 = x0 + w, y1 = y0 + h;
+  const bool out_x = (cx < x0) || (cx > x1), out_y = (cy < y0) || (cy > y1);
+  if (!out_x && !out_y) return true;
+  float qmin = 3.0e38f;
+  if (out_x) {
+    const float dx = ((cx < x0) ? x0 : x1) - cx;
+    const float ys = fminf(fmaxf(cy - (B / C) * dx, y0), y1);
+    const float dy = ys - cy;
+    qmin = 0.5f * (A * dx * dx + C * dy * dy) + B * dx * dy;
+  }
+  if (out_y) {
+    const float dy = ((cy < y0) ? y0 : y1) - cy;
+    const float xs = fminf(fmaxf(cx - (B / A) * dy, x0), x1);
+    const float dx = xs - cx;
+    qmin = fminf(qmin, 0.5f * (A * dx * dx + C * dy * dy) + B * dx * dy);
+  }
+  return qmin * 0.9995f <= tau;
+}
+
 __device__ const float kShC0 = 0.28209479177387814f;
 __device__ const float kShC1 = 0.4886025119029199f;
 __device__ const float kShC2[5] = {1.0925484305920792f, -1.0925484305920792f, 0.31539156525252005f,

@@ -68,6 +68,7 @@ preprocess_kernel(PreArgs a, int32_t* __restrict__ radii, uint8_t* __restrict__ 
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= a.P) return;
   radii[idx] = 0;
+  is_used[idx] = 0;
   tiles_touched[idx] = 0;
   depth_key[idx] = kInvisibleKey;
   ident[idx] = idx;
@@ -199,25 +200,12 @@ __global__ void tile_ranges_kernel(int R, const KeyT* __restrict__ keys, uint2* 
 //
 // Per batch of 256 tile instances the CTA stages the 48-B splat records in shared memory with
 // 128-bit loads (one instance per thread).  Each warp then culls the batch against its own 8x4
-// pixel rectangle — lane l tests instance 32*chunk+l: the axis-aligned bounding box of the
-// ellipse {alpha >= 1/255} — and only the survivors (ballot mask) are evaluated by all 32 lanes.
+// pixel rectangle — lane l tests instance 32*chunk+l: the exact minimum of the conic's
+// quadratic form over the rectangle against ln(255*opacity) (raster_common.cuh: subtile_hit) — and only the survivors (ballot mask) are evaluated by all 32 lanes.
 // Culled instances are exactly those the reference skips for every pixel of the sub-tile
 // (power > 0 or alpha < 1/255, forward.cu:359-366), so the blend result is unchanged while the
 // pixel-Gaussian pair count drops by the ratio (bounding-square tiles) / (ellipse ∩ sub-tiles).
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool subtile_hit(const float4 a, const float4 b, float wx0, float wy0) {
-  const float A = a.z, B = a.w, C = b.x, o = b.y;
-  const float det = A * C - B * B;
-  const float t255 = 255.f * o;
-  if (!(t255 >= 0.999f)) return false;  // alpha = o * exp(power <= 0) can never reach 1/255
-  if (!(A > 0.f && C > 0.f && det > 0.f)) return true;  // not an ellipse: do not cull
-  const float tau = fmaxf(__logf(t255), 0.f) * 1.001f + 2e-3f;  // power >= -tau  <=>  alpha >= 1/255 (with margin)
-  const float inv = 2.f * tau / det;
-  const float hx = sqrtf(inv * C) * 1.0005f + 1e-3f;
-  const float hy = sqrtf(inv * A) * 1.0005f + 1e-3f;
-  return (a.x + hx >= wx0) && (a.x - hx <= wx0 + 7.f) && (a.y + hy >= wy0) && (a.y - hy <= wy0 + 3.f);
-}
-
 template <bool kCull>
 __global__ void __launch_bounds__(kTilePixels)
 render_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H,
@@ -258,7 +246,7 @@ render_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
       uint32_t mask;
       if (kCull) {
         const int j = c0 + lane;
-        const bool hit = (j < n) && subtile_hit(sA[j], sB[j], (float)wx0, (float)wy0);
+        const bool hit = (j < n) && subtile_hit(sA[j], sB[j], (float)wx0, (float)wy0, 7.f, 3.f);
         mask = __ballot_sync(0xffffffffu, hit);
       } else {
         mask = (n - c0 >= 32) ? 0xffffffffu : ((1u << (n - c0)) - 1u);

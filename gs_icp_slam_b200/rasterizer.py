@@ -97,10 +97,13 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
     dev = means3D.device
     P, H, W = means3D.size(0), int(image_height), int(image_width)
     with torch.cuda.device(dev):
-        out_depth = torch.zeros((1, H, W), dtype=torch.float32, device=dev)
-        out_color = torch.zeros((NUM_CHANNELS, H, W), dtype=torch.float32, device=dev)
-        radii = torch.zeros((P,), dtype=torch.int32, device=dev)
-        is_used = torch.zeros((P,), dtype=torch.bool, device=dev)
+        # The kernels write every element of the four outputs when P > 0 and all tiles are rendered here, so no
+        # zero-fill launches are needed (the reference fills them: rasterize_points.cu:65-68).
+        alloc = torch.empty if (P != 0 and _tile_shard[0] == 1) else torch.zeros
+        out_depth = alloc((1, H, W), dtype=torch.float32, device=dev)
+        out_color = alloc((NUM_CHANNELS, H, W), dtype=torch.float32, device=dev)
+        radii = alloc((P,), dtype=torch.int32, device=dev)
+        is_used = alloc((P,), dtype=torch.bool, device=dev)
         bufs = _Buffers(dev)
         rendered = 0
         if P != 0:
@@ -131,12 +134,19 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
     H, W = dL_dout_color.size(1), dL_dout_color.size(2)
     M = sh.size(1) if sh.numel() != 0 else 0
     with torch.cuda.device(dev):
-        z = lambda *s: torch.zeros(s, dtype=torch.float32, device=dev)
-        dL_dmeans3D, dL_dmeans2D, dL_dcolors = z(P, 3), z(P, 3), z(P, NUM_CHANNELS)
-        dL_dopacity, dL_dcov3D, dL_dsh = z(P, 1), z(P, 6), z(P, M, 3)
-        dL_dscales, dL_drotations = z(P, 3), z(P, 4)
+        # one zero-filled slab for the eight gradient tensors and the work buffer (one fill launch instead of nine)
+        shapes = [(P, 3), (P, 3), (P, NUM_CHANNELS), (P, 1), (P, 6), (P, M, 3), (P, 3), (P, 4)]
+        sizes = [int(torch.Size(shp).numel()) for shp in shapes]
+        pad = lambda n: (n + 3) // 4 * 4  # keep every view 16-byte aligned
+        work_n = (int(lib.gsicp_raster_backward_work_bytes(P)) // 4) if P != 0 else 0
+        slab = torch.zeros(sum(pad(n) for n in sizes) + work_n, dtype=torch.float32, device=dev)
+        views, off = [], 0
+        for shp, n in zip(shapes, sizes):
+            views.append(slab[off:off + n].view(shp))
+            off += pad(n)
+        dL_dmeans3D, dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations = views
         if P != 0:
-            work = torch.zeros(int(lib.gsicp_raster_backward_work_bytes(P)) // 4, dtype=torch.float32, device=dev)
+            work = slab[off:off + work_n]
             keep = [_f32c(x, dev) for x in (background, means3D, sh, colors, None, scales, rotations, cov3D_precomp,
                                             viewmatrix, projmatrix, campos, dL_dout_color, dL_dout_depth)]
             bg, m3, shc, col, _, sc, rot, cov, view, proj, cam, gcol, gdep = keep

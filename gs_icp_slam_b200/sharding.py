@@ -1,0 +1,65 @@
+"""Multi-GPU host logic: one process per GPU, torch.distributed (NCCL on the GPUs, gloo in the CPU tests).
+
+* rasterizer: screen tiles are interleaved over the ranks (tile % world == rank).  Every rank preprocesses all Gaussians
+  but emits / sorts / renders only its own tiles; the loss is evaluated on the rank's own pixels with the GLOBAL
+  normalisation, so the per-Gaussian parameter gradients of the ranks simply add: one all-reduce per iteration.
+* GICP: source points are split into contiguous ranges; the 28 doubles of the normal equations (21 H + 6 b + error)
+  are all-reduced before the (replicated) host LM step reads them.
+"""
+import torch
+
+TILE = 16
+
+
+def tile_owner_mask(height, width, world, rank, device="cpu"):
+    """float32 [1,H,W]: 1 where the pixel's 16x16 tile belongs to `rank` (tile_id % world == rank)."""
+    ty, tx = (height + TILE - 1) // TILE, (width + TILE - 1) // TILE
+    tid = torch.arange(ty, device=device)[:, None] * tx + torch.arange(tx, device=device)[None, :]
+    own = (tid % world == rank).repeat_interleave(TILE, 0).repeat_interleave(TILE, 1)[:height, :width]
+    return own.float()[None]
+
+
+def source_range(n, world, rank):
+    """[begin, end) of the source points rank `rank` linearises — must match shard_range() in csrc/gicp.cu."""
+    per = (n + world - 1) // world
+    return min(n, per * rank), min(n, per * (rank + 1))
+
+
+def sharded_l1(pred, target, mask, n_total):
+    """sum |pred - target| over the rank's pixels divided by the global element count: the rank's share of a mean L1."""
+    return ((pred - target).abs() * mask).sum() / float(n_total)
+
+
+def allreduce_grads(params, group=None):
+    """Sum the .grad of every tensor in `params` over the ranks with ONE collective (flat buffer)."""
+    import torch.distributed as dist
+
+    grads = [p.grad for p in params if p.grad is not None]
+    if not grads:
+        return
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat, group=group)
+    off = 0
+    for g in grads:
+        n = g.numel()
+        g.copy_(flat[off:off + n].view_as(g))
+        off += n
+
+
+class DevicePtrArray:
+    """Zero-copy view of `count` float64 values at a raw device pointer (CUDA array interface), so the library's
+    reduction buffer can be handed to torch.distributed.all_reduce."""
+
+    def __init__(self, ptr, count):
+        self.__cuda_array_interface__ = {"shape": (int(count),), "typestr": "<f8", "data": (int(ptr), False), "version": 3}
+
+
+def make_gicp_allreduce(device, group=None):
+    """Callback for FastGICP.set_shard: all-reduces the library's fp64 buffer in place over `group`."""
+    import torch.distributed as dist
+
+    def cb(ptr, count, stream):
+        t = torch.as_tensor(DevicePtrArray(ptr, count), device=device)
+        dist.all_reduce(t, group=group)
+
+    return cb
