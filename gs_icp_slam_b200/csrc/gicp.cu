@@ -201,9 +201,15 @@ __device__ __forceinline__ double warp_sum_d(double v) {
 
 // block-level reduction of NV doubles per thread into partial[blockIdx][NV]; the last block to finish
 // sums the partials in block order (deterministic) into out[NV].
+//
+// When `host_out` is non-null (single-GPU runs) the last block also publishes the sums into MAPPED PINNED host memory and
+// then bumps a sequence word the host spins on: the result reaches the LM loop without a D2H memcpy or a
+// cudaStreamSynchronize round trip (two driver calls and a thread wake-up per launch otherwise).
 template <int NV>
 __device__ __forceinline__ void block_reduce_finalize(double* v, double* __restrict__ partial, double* __restrict__ out,
-                                                      unsigned int* __restrict__ counter) {
+                                                      unsigned int* __restrict__ counter, double* host_out = nullptr,
+                                                      volatile unsigned long long* host_seq = nullptr,
+                                                      unsigned long long seq = 0) {
   __shared__ double s_red[kLinBlock / 32][NV];
   __shared__ bool s_last;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -232,8 +238,19 @@ __device__ __forceinline__ void block_reduce_finalize(double* v, double* __restr
       double r = 0.0;
       for (unsigned int b = 0; b < gridDim.x; b++) r += partial[(size_t)b * NV + threadIdx.x];
       out[threadIdx.x] = r;
+      if (host_out) host_out[threadIdx.x] = r;
     }
-    if (threadIdx.x == 0) *counter = 0u;  // ready for the next launch
+    if (host_out) {
+      __threadfence_system();
+      __syncthreads();  // s_last is block-uniform
+    }
+    if (threadIdx.x == 0) {
+      *counter = 0u;  // ready for the next launch
+      if (host_seq) {
+        *host_seq = seq;
+        __threadfence_system();
+      }
+    }
   }
 }
 
@@ -250,6 +267,9 @@ struct LinArgs {
   double* partial;
   double* out;             // [28]
   unsigned int* counter;
+  double* host_out;        // mapped pinned [28] or null
+  volatile unsigned long long* host_seq;
+  unsigned long long seq;
 };
 
 constexpr int kLinGroup = 4;  // lanes cooperating on one source point's nearest-neighbour search
@@ -347,7 +367,7 @@ linearize_kernel(GridView tgt, PoseD T, LinArgs a) {
       }
     }
   }
-  block_reduce_finalize<kRed>(v, a.partial, a.out, a.counter);
+  block_reduce_finalize<kRed>(v, a.partial, a.out, a.counter, a.host_out, a.host_seq, a.seq);
 }
 
 struct ErrArgs {
@@ -359,6 +379,9 @@ struct ErrArgs {
   double* partial;
   double* out;  // [1]
   unsigned int* counter;
+  double* host_out;
+  volatile unsigned long long* host_seq;
+  unsigned long long seq;
 };
 
 __global__ void __launch_bounds__(kLinBlock)
@@ -382,7 +405,7 @@ error_kernel(PoseD T, ErrArgs a) {
       v[0] = (e[0] * Me0 + e[1] * Me1) + e[2] * Me2;
     }
   }
-  block_reduce_finalize<1>(v, a.partial, a.out, a.counter);
+  block_reduce_finalize<1>(v, a.partial, a.out, a.counter, a.host_out, a.host_seq, a.seq);
 }
 
 __global__ void f64_to_f32_kernel(size_t n, const double* __restrict__ in, float* __restrict__ out) {
@@ -534,6 +557,9 @@ struct gsicp_gicp {
   Scratch corr, sqd, mahal, partial, red_out, counter, staging_dev, nn_id, nn_d2;
   int corr_n = 0;
   double* h_red = nullptr;     // pinned [28]
+  unsigned long long* h_map = nullptr;  // mapped pinned: [0..27] sums (as double), [28] sequence word
+  unsigned long long* d_map = nullptr;  // device alias of h_map
+  unsigned long long seq = 0;
   void* h_stage = nullptr;     // pinned staging for H2D conversions
   size_t h_stage_cap = 0;
   int shard_count = 1, shard_index = 0;
@@ -588,10 +614,8 @@ int set_cloud(gsicp_gicp* h, Cloud& c, const void* xyz, int n, int is_f32, bool 
   if (device_src) {
     GSICP_CUDA(cudaMemcpyAsync(c.xyz.ptr, xyz, cnt * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
   } else if (is_f32) {
-    if (int e = ensure_stage(h, cnt * sizeof(float))) return e;
-    GSICP_CUDA(cudaStreamSynchronize(h->stream));  // staging buffer reuse
-    std::memcpy(h->h_stage, xyz, cnt * sizeof(float));
-    GSICP_CUDA(cudaMemcpyAsync(c.xyz.ptr, h->h_stage, cnt * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    // pageable float32 source: the runtime stages it in chunks itself — no extra host copy, no stream sync
+    GSICP_CUDA(cudaMemcpyAsync(c.xyz.ptr, xyz, cnt * sizeof(float), cudaMemcpyHostToDevice, h->stream));
   } else {
     // float64 from numpy (main.cpp:37-45 eigen2pcl casts to float): convert while staging
     if (int e = ensure_stage(h, cnt * sizeof(float))) return e;
@@ -614,10 +638,8 @@ int set_filter(gsicp_gicp* h, Cloud& c, int num_trackable, const int32_t* filter
   c.filter_n = n;
   if (n == 0) return GSICP_OK;
   if (int e = c.filter.ensure((size_t)n * 4)) return e;
-  if (int e = ensure_stage(h, (size_t)n * 4)) return e;
-  GSICP_CUDA(cudaStreamSynchronize(h->stream));
-  std::memcpy(h->h_stage, filter, (size_t)n * 4);
-  GSICP_CUDA(cudaMemcpyAsync(c.filter.ptr, h->h_stage, (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
+  // pageable source: the runtime stages it before returning, so no pinned staging buffer (and no sync) is needed
+  GSICP_CUDA(cudaMemcpyAsync(c.filter.ptr, filter, (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
   return GSICP_OK;
 }
 
@@ -700,14 +722,8 @@ int covs_from_qs(gsicp_gicp* h, Cloud& c, const float* rots, const float* scales
                  c.cov.as<double>());
     GSICP_CUDA(cudaGetLastError());
   } else if (n > 0) {
-    if (int e = ensure_stage(h, (size_t)n * 7 * sizeof(float))) return e;
-    GSICP_CUDA(cudaStreamSynchronize(h->stream));
-    float* st = (float*)h->h_stage;
-    std::memcpy(st, rots, (size_t)n * 4 * sizeof(float));
-    std::memcpy(st + (size_t)n * 4, scales, (size_t)n * 3 * sizeof(float));
-    GSICP_CUDA(cudaMemcpyAsync(c.rots.ptr, st, (size_t)n * 4 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
-    GSICP_CUDA(cudaMemcpyAsync(c.scales.ptr, st + (size_t)n * 4, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice,
-                               h->stream));
+    GSICP_CUDA(cudaMemcpyAsync(c.rots.ptr, rots, (size_t)n * 4 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    GSICP_CUDA(cudaMemcpyAsync(c.scales.ptr, scales, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
     GSICP_LAUNCH(cov_from_qs_kernel, (n + 255) / 256, 256, 0, h->stream, n, c.rots.as<float>(), c.scales.as<float>(),
                  c.cov.as<double>());
     GSICP_CUDA(cudaGetLastError());
@@ -742,6 +758,34 @@ int ensure_lin_buffers(gsicp_gicp* h) {
     GSICP_CUDA(cudaMemsetAsync(h->counter.ptr, 0, sizeof(unsigned int), h->stream));
   }
   if (!h->h_red) GSICP_CUDA(cudaMallocHost(&h->h_red, kRed * sizeof(double)));
+  if (!h->h_map) {
+    GSICP_CUDA(cudaHostAlloc((void**)&h->h_map, 32 * sizeof(unsigned long long), cudaHostAllocMapped));
+    std::memset(h->h_map, 0, 32 * sizeof(unsigned long long));
+    GSICP_CUDA(cudaHostGetDevicePointer((void**)&h->d_map, h->h_map, 0));
+  }
+  return GSICP_OK;
+}
+
+// Spin until the kernel's last block has published sequence number `seq` into mapped host memory.
+int wait_published(gsicp_gicp* h, unsigned long long seq) {
+  volatile unsigned long long* p = h->h_map + 28;
+  long spins = 0;
+  while (*p != seq) {
+#if defined(__x86_64__)
+    __builtin_ia32_pause();
+#endif
+    if ((++spins & 0xfffff) == 0) {  // every ~1M spins make sure the kernel has not failed
+      const cudaError_t q = cudaStreamQuery(h->stream);
+      if (q != cudaSuccess && q != cudaErrorNotReady) {
+        set_error("kernel failed: %s", cudaGetErrorString(q));
+        return GSICP_ECUDA;
+      }
+      if (q == cudaSuccess && *p != seq) {
+        set_error("reduction result was not published");
+        return GSICP_ECUDA;
+      }
+    }
+  }
   return GSICP_OK;
 }
 
@@ -764,6 +808,10 @@ int run_linearize(gsicp_gicp* h, const Iso& x, double H[6][6], double b[6], doub
   a.tgt_xyz = h->tgt.xyz.as<float>(); a.tgt_cov = h->tgt.cov.as<double>();
   a.corr = h->corr.as<int32_t>(); a.sqd = h->sqd.as<float>(); a.mahal = h->mahal.as<double>();
   a.partial = h->partial.as<double>(); a.out = h->red_out.as<double>(); a.counter = h->counter.as<unsigned int>();
+  const bool direct = (h->shard_count <= 1) && !h->timing;  // publish straight into mapped host memory
+  a.host_out = direct ? (double*)h->d_map : nullptr;
+  a.host_seq = direct ? (volatile unsigned long long*)(h->d_map + 28) : nullptr;
+  a.seq = ++h->seq;
   int blocks = (int)(((size_t)(end - begin) * kLinGroup + kLinBlock - 1) / kLinBlock);
   if (blocks < 1) blocks = 1;
   { ProfScope ps(kProfLinearize, h->stream);
@@ -775,9 +823,15 @@ int run_linearize(gsicp_gicp* h, const Iso& x, double H[6][6], double b[6], doub
       return GSICP_ECUDA;
     }
   }
-  GSICP_CUDA(cudaMemcpyAsync(h->h_red, h->red_out.ptr, kRed * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-  tm.stop();
-  GSICP_CUDA(cudaStreamSynchronize(h->stream));
+  if (direct) {
+    GSICP_CUDA(cudaGetLastError());
+    if (int e = wait_published(h, a.seq)) return e;
+    std::memcpy(h->h_red, h->h_map, kRed * sizeof(double));
+  } else {
+    GSICP_CUDA(cudaMemcpyAsync(h->h_red, h->red_out.ptr, kRed * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    tm.stop();
+    GSICP_CUDA(cudaStreamSynchronize(h->stream));
+  }
   h->n_lin++;
   if (H && b) {
     int o = 0;
@@ -803,6 +857,10 @@ int run_error(gsicp_gicp* h, const Iso& x, double* err) {  // fgi:355-378
   a.src_xyz = h->src.xyz.as<float>(); a.tgt_xyz = h->tgt.xyz.as<float>();
   a.corr = h->corr.as<int32_t>(); a.mahal = h->mahal.as<double>();
   a.partial = h->partial.as<double>(); a.out = h->red_out.as<double>(); a.counter = h->counter.as<unsigned int>();
+  const bool direct = (h->shard_count <= 1) && !h->timing;
+  a.host_out = direct ? (double*)h->d_map : nullptr;
+  a.host_seq = direct ? (volatile unsigned long long*)(h->d_map + 28) : nullptr;
+  a.seq = ++h->seq;
   int blocks = (end - begin + kLinBlock - 1) / kLinBlock;
   if (blocks < 1) blocks = 1;
   { ProfScope ps(kProfError, h->stream);
@@ -811,9 +869,15 @@ int run_error(gsicp_gicp* h, const Iso& x, double* err) {  // fgi:355-378
     const int rc = h->reduce(h->reduce_user, h->red_out.as<double>(), 1, (void*)h->stream);
     if (rc != 0) return GSICP_ECUDA;
   }
-  GSICP_CUDA(cudaMemcpyAsync(h->h_red, h->red_out.ptr, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-  tm.stop();
-  GSICP_CUDA(cudaStreamSynchronize(h->stream));
+  if (direct) {
+    GSICP_CUDA(cudaGetLastError());
+    if (int e = wait_published(h, a.seq)) return e;
+    h->h_red[0] = *(const double*)h->h_map;
+  } else {
+    GSICP_CUDA(cudaMemcpyAsync(h->h_red, h->red_out.ptr, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    tm.stop();
+    GSICP_CUDA(cudaStreamSynchronize(h->stream));
+  }
   h->n_err++;
   *err = h->h_red[0];
   return GSICP_OK;
@@ -921,6 +985,7 @@ void gsicp_gicp_destroy(gsicp_gicp* h) {
   }
   fr(h->corr); fr(h->sqd); fr(h->mahal); fr(h->partial); fr(h->red_out); fr(h->counter); fr(h->staging_dev); fr(h->nn_id); fr(h->nn_d2);
   if (h->h_red) cudaFreeHost(h->h_red);
+  if (h->h_map) cudaFreeHost(h->h_map);
   if (h->h_stage) cudaFreeHost(h->h_stage);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
@@ -1044,8 +1109,12 @@ int gsicp_gicp_get_source_correspondence(gsicp_gicp* h, int32_t* corr, float* sq
     set_error("no correspondences for the current source cloud");
     return GSICP_ESTATE;
   }
-  if (int e = copy_out(h, h->corr, (size_t)h->src.n * 4, corr)) return e;
-  return copy_out(h, h->sqd, (size_t)h->src.n * 4, sq_dist);
+  if (h->src.n == 0) return GSICP_OK;
+  if (!corr || !sq_dist) return GSICP_EINVAL;
+  GSICP_CUDA(cudaMemcpyAsync(corr, h->corr.ptr, (size_t)h->src.n * 4, cudaMemcpyDeviceToHost, h->stream));
+  GSICP_CUDA(cudaMemcpyAsync(sq_dist, h->sqd.ptr, (size_t)h->src.n * 4, cudaMemcpyDeviceToHost, h->stream));
+  GSICP_CUDA(cudaStreamSynchronize(h->stream));
+  return GSICP_OK;
 }
 
 static int pose_from16(const double p[16], Iso& x) {

@@ -146,32 +146,27 @@ render_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restr
             // depth: same alpha and transmittance as colour (T_d == T bit for bit)
             const float czx = b.z, cyz = b.w;
             const float depth = c.w - (czx * a.z + cyz * a.w) * dx - (czx * a.w + cyz * b.x) * dy;
-            g[3] = w * dpd;
-            const float d_covzx = (-a.z * dx - a.w * dy) * w;
-            const float d_covyz = (-a.w * dx) * w;  // reference omits the conic_yy*dy term (backward.cu:616)
-            const float d_conx = (-czx * dx) * w;
-            const float d_cony = (-cyz * dx - czx * dy) * w;
-            const float d_conz = (-cyz * dy) * w;
-            const float d_delx = -(czx * a.z + cyz * a.w) * w;
-            const float d_dely = -(czx * a.w + cyz * b.x) * w;
             last_depth = depth;
             last_alpha = alpha;
             float dL_dalpha_d = dpd * ((depth - acc_d) * T);
             dL_dalpha_d += (-T_final / (1.f - alpha)) * bg_dot_ddepth;
 
-            const float dL_dG = b.y * dL_dalpha;
-            const float dL_dG_d = b.y * dL_dalpha_d;
-            const float gdx = G * dx, gdy = G * dy;
-            const float dG_ddelx = -gdx * a.z - gdy * a.w;
-            const float dG_ddely = -gdy * b.x - gdx * a.w;
-            g[4] = dL_dG * dG_ddelx * ddelx_dx + dL_dG_d * dG_ddelx * ddelx_dx + dpd * d_delx * ddelx_dx;
-            g[5] = dL_dG * dG_ddely * ddely_dy + dL_dG_d * dG_ddely * ddely_dy + dpd * d_dely * ddely_dy;
-            g[6] = -0.5f * gdx * dx * dL_dG - 0.5f * gdx * dx * dL_dG_d + dpd * d_conx;
-            g[7] = -0.5f * gdx * dy * dL_dG - 0.5f * gdx * dy * dL_dG_d + dpd * d_cony;
-            g[8] = -0.5f * gdy * dy * dL_dG - 0.5f * gdy * dy * dL_dG_d + dpd * d_conz;
-            g[9] = dpd * d_covzx;
-            g[10] = dpd * d_covyz;
-            g[11] = G * dL_dalpha + G * dL_dalpha_d;
+            // Per pair only 12 MOMENTS are accumulated; the reference's 12 gradient expressions (backward.cu:575-654)
+            // are linear in them with per-Gaussian coefficients and are formed once per (tile, instance) at flush time:
+            //   t = G (dL/dalpha + dL/dalpha_d),  u = opacity * t  (= dL_dG + dL_dG_d times G),  v = alpha T dL/dpix_depth
+            const float t = G * (dL_dalpha + dL_dalpha_d);
+            const float u = b.y * t;
+            const float v = w * dpd;
+            const float udx = u * dx, udy = u * dy;
+            g[3] = v;
+            g[4] = t;
+            g[5] = udx;
+            g[6] = udy;
+            g[7] = udx * dx;
+            g[8] = udx * dy;
+            g[9] = udy * dy;
+            g[10] = v * dx;
+            g[11] = v * dy;
           }
           {
             if (__popc(act) <= 2) {
@@ -207,22 +202,28 @@ render_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restr
       }
     }
     __syncthreads();
-    // flush: one set of global atomics per (tile, instance) that received anything
+    // flush: form the 12 gradients of each touched instance from its moments and issue one set of global atomics
     if (tid < n && ((sTouched[tid >> 5] >> (tid & 31)) & 1u)) {
       const uint32_t gid = sId[tid];
-      atomicAdd(&dL_dcolors[3 * (size_t)gid + 0], sAcc[0 * kTilePixels + tid]);
-      atomicAdd(&dL_dcolors[3 * (size_t)gid + 1], sAcc[1 * kTilePixels + tid]);
-      atomicAdd(&dL_dcolors[3 * (size_t)gid + 2], sAcc[2 * kTilePixels + tid]);
+      const float4 a = sA[tid], b = sB[tid];
+      const float A = a.z, B = a.w, C = b.x, czx = b.z, cyz = b.w;
+      float m[kG];
+#pragma unroll
+      for (int k = 0; k < kG; k++) m[k] = sAcc[k * kTilePixels + tid];
+      const float v0 = m[3], tt = m[4], ux = m[5], uy = m[6], uxx = m[7], uxy = m[8], uyy = m[9], vx = m[10], vy = m[11];
+      atomicAdd(&dL_dcolors[3 * (size_t)gid + 0], m[0]);
+      atomicAdd(&dL_dcolors[3 * (size_t)gid + 1], m[1]);
+      atomicAdd(&dL_dcolors[3 * (size_t)gid + 2], m[2]);
       float* wk = work + 8 * (size_t)gid;
-      atomicAdd(&wk[5], sAcc[3 * kTilePixels + tid]);
-      atomicAdd(&dL_dmean2D[3 * (size_t)gid + 0], sAcc[4 * kTilePixels + tid]);
-      atomicAdd(&dL_dmean2D[3 * (size_t)gid + 1], sAcc[5 * kTilePixels + tid]);
-      atomicAdd(&wk[0], sAcc[6 * kTilePixels + tid]);
-      atomicAdd(&wk[1], sAcc[7 * kTilePixels + tid]);
-      atomicAdd(&wk[2], sAcc[8 * kTilePixels + tid]);
-      atomicAdd(&wk[3], sAcc[9 * kTilePixels + tid]);
-      atomicAdd(&wk[4], sAcc[10 * kTilePixels + tid]);
-      atomicAdd(&dL_dopacity[gid], sAcc[11 * kTilePixels + tid]);
+      atomicAdd(&wk[5], v0);                                                                   // dL/ddepth
+      atomicAdd(&dL_dmean2D[3 * (size_t)gid + 0], (-A * ux - B * uy - (czx * A + cyz * B) * v0) * ddelx_dx);
+      atomicAdd(&dL_dmean2D[3 * (size_t)gid + 1], (-C * uy - B * ux - (czx * B + cyz * C) * v0) * ddely_dy);
+      atomicAdd(&wk[0], -0.5f * uxx - czx * vx);                                               // dL/dconic_xx
+      atomicAdd(&wk[1], -0.5f * uxy - cyz * vx - czx * vy);                                    // dL/dconic_xy
+      atomicAdd(&wk[2], -0.5f * uyy - cyz * vy);                                               // dL/dconic_yy
+      atomicAdd(&wk[3], -A * vx - B * vy);                                                     // dL/dcov_zx
+      atomicAdd(&wk[4], -B * vx);  // dL/dcov_yz: the reference omits the conic_yy * dy term (backward.cu:616)
+      atomicAdd(&dL_dopacity[gid], tt);
     }
   }
 }

@@ -255,27 +255,24 @@ render_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
         const int bit = __ffs(mask) - 1;
         mask &= mask - 1;
         const int j = c0 + bit;
-        if (done) continue;
-        const float4 a = sA[j], b = sB[j];
+        // Branch-free blend step: every lane evaluates the instance, the state update is predicated.  The
+        // expressions keep the reference's shape ((c * alpha) * T, forward.cu:373-375,400) so results match bit for bit.
+        const float4 a = sA[j], b = sB[j], c = sC[j];
         const float dx = a.x - pxf, dy = a.y - pyf;
         const float power = -0.5f * (a.z * dx * dx + b.x * dy * dy) - a.w * dx * dy;
-        if (power > 0.0f) continue;
         const float alpha = fminf(0.99f, b.y * expf(power));
-        if (alpha < 1.0f / 255.0f) continue;
         const float test_T = T * (1 - alpha);
-        if (test_T < 0.0001f) {
-          done = true;  // colour and depth both stop here (forward.cu:367-383,392-393)
-          continue;
-        }
-        const float4 c = sC[j];
-        Cr += c.x * alpha * T;
-        Cg += c.y * alpha * T;
-        Cb += c.z * alpha * T;
+        const bool hit = !done && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
+        const bool blend = hit && !(test_T < 0.0001f);
+        done = done || (hit && !blend);  // colour and depth both stop here (forward.cu:367-383,392-393)
         // depth conditioned on the pixel offset through the z cross-covariances (forward.cu:395-399)
         const float dcond = c.w - (b.z * a.z + b.w * a.w) * dx - (b.z * a.w + b.w * b.x) * dy;
-        D += dcond * alpha * T;
-        T = test_T;
-        last = (uint32_t)(base + j + 1);
+        Cr = blend ? (Cr + c.x * alpha * T) : Cr;
+        Cg = blend ? (Cg + c.y * alpha * T) : Cg;
+        Cb = blend ? (Cb + c.z * alpha * T) : Cb;
+        D = blend ? (D + dcond * alpha * T) : D;
+        T = blend ? test_T : T;
+        last = blend ? (uint32_t)(base + j + 1) : last;
       }
       if (__all_sync(0xffffffffu, done)) break;
     }
@@ -291,6 +288,15 @@ render_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
     out_color[1 * HW + pix] = Cg + T * bg[1];
     out_color[2 * HW + pix] = Cb + T * bg[2];
   }
+}
+
+// publishes the instance count into mapped pinned host memory, then bumps the sequence word the host spins on
+__global__ void publish_count_kernel(const uint32_t* __restrict__ last_offset, volatile unsigned long long* host_map,
+                                     unsigned long long seq) {
+  host_map[0] = (unsigned long long)(*last_offset);
+  __threadfence_system();
+  host_map[1] = seq;
+  __threadfence_system();
 }
 
 __global__ void mark_visible_kernel(int P, const float* __restrict__ means, const float* __restrict__ view,
@@ -314,7 +320,9 @@ __global__ void copy_ranges_kernel(int tiles, const uint2* __restrict__ ranges, 
 struct FwdScratch {
   std::mutex mu;
   Scratch per_gaussian, per_instance, cub_tmp;
-  int* h_count = nullptr;  // pinned
+  unsigned long long* h_map = nullptr;  // mapped pinned: [0] = num_rendered, [1] = sequence word
+  unsigned long long* d_map = nullptr;
+  unsigned long long seq = 0;
 };
 static FwdScratch g_fwd;
 
@@ -368,7 +376,11 @@ extern "C" int gsicp_raster_forward(const gsicp_raster_args* args, float* d_out_
   ImgState img = ImgState::from(img_p, N, tiles);
 
   std::lock_guard<std::mutex> lock(g_fwd.mu);
-  if (!g_fwd.h_count) GSICP_CUDA(cudaMallocHost(&g_fwd.h_count, sizeof(int)));
+  if (!g_fwd.h_map) {
+    GSICP_CUDA(cudaHostAlloc((void**)&g_fwd.h_map, 2 * sizeof(unsigned long long), cudaHostAllocMapped));
+    g_fwd.h_map[0] = g_fwd.h_map[1] = 0;
+    GSICP_CUDA(cudaHostGetDevicePointer((void**)&g_fwd.d_map, g_fwd.h_map, 0));
+  }
 
   int R = 0;
   uint32_t *depth_key = nullptr, *ident = nullptr, *depth_sorted = nullptr, *order = nullptr, *tiles_touched = nullptr,
@@ -422,9 +434,31 @@ extern "C" int gsicp_raster_forward(const gsicp_raster_args* args, float* d_out_
 
     // The Python API returns num_rendered as a host int (DGR/diff_gaussian_rasterization/__init__.py:96),
     // and the instance buffers are sized by it: one 4-byte D2H + sync, as in rasterizer_impl.cu:286-287.
-    GSICP_CUDA(cudaMemcpyAsync(g_fwd.h_count, offsets + (P - 1), sizeof(int), cudaMemcpyDeviceToHost, stream));
-    GSICP_CUDA(cudaStreamSynchronize(stream));
-    R = *g_fwd.h_count;
+    // The count travels through mapped pinned memory + a sequence word the host spins on (no memcpy / stream-sync calls).
+    const unsigned long long seq = ++g_fwd.seq;
+    GSICP_LAUNCH(publish_count_kernel, 1, 1, 0, stream, offsets + (P - 1), (volatile unsigned long long*)g_fwd.d_map, seq);
+    GSICP_CUDA(cudaGetLastError());
+    {
+      volatile unsigned long long* pm = g_fwd.h_map;
+      long spins = 0;
+      while (pm[1] != seq) {
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+        if ((++spins & 0xfffff) == 0) {
+          const cudaError_t q = cudaStreamQuery(stream);
+          if (q != cudaSuccess && q != cudaErrorNotReady) {
+            set_error("rasterizer forward failed before binning: %s", cudaGetErrorString(q));
+            return GSICP_ECUDA;
+          }
+          if (q == cudaSuccess && pm[1] != seq) {
+            set_error("instance count was not published");
+            return GSICP_ECUDA;
+          }
+        }
+      }
+      R = (int)pm[0];
+    }
     if (R < 0) {
       set_error("gsicp_raster_forward: instance count overflow");
       return GSICP_EINVAL;
