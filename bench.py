@@ -254,6 +254,8 @@ class Ours:
     def enable_overlap(self):
         from concurrent.futures import ThreadPoolExecutor
 
+        # two Python threads hand the GIL over every switch interval (default 5 ms) when both want it: make it short
+        sys.setswitchinterval(2e-5)
         self.pool = ThreadPoolExecutor(max_workers=1)
         self.gicp_stream = self.torch.cuda.Stream(device=self.dev)
         self.reg.set_stream(self.gicp_stream.cuda_stream)
@@ -433,6 +435,10 @@ def main():
         eng.enable_overlap()
     from gs_icp_slam_b200 import _lib
 
+    # untimed pre-pass: CUDA module loading, caching-allocator growth and library scratch growth happen here, not in
+    # the W warm-up steps of the first timed pass
+    eng.run(min(args.steps, 5), 1, resident=False)
+    eng.run(min(args.steps, 5), 1, resident=True)
     with ClockSampler(local_rank) as clk:
         t_res, launches, st_res = eng.run(args.steps, args.warmup, resident=True)
         t_e2e, _, st_e2e = eng.run(args.steps, args.warmup, resident=False)

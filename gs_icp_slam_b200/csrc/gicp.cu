@@ -7,9 +7,10 @@
 //   covariance_kernel   fgi:382-479 / 588-706 / 710-825  k-NN (exact, grid) -> mean -> cov/k -> Jacobi SVD
 //                       -> quaternion(U), sqrt(sigma) -> NORMALIZED_ELLIPSE covariance (+ filter compaction)
 //   cov_from_qs_kernel  fgi:828-902  covariances from (quaternion, scale) incl. the (w,x,y,z) ctor quirk
-//   linearize_kernel    fgi:242-293 + 296-352 fused: fp32 transform -> exact 1-NN -> Mahalanobis
-//                       (RCR^-1) -> e, J=[skew(Tp) | -I] -> 28-double block reduction (21 H + 6 b + err),
-//                       deterministic last-block finalisation
+//   correspond_kernel   fgi:242-272  warp per source point: fp32 transform -> exact 1-NN (coalesced cell-row scans)
+//   linearize_kernel    fgi:273-293 + 296-352  thread per source point: Mahalanobis (RCR^-1) -> e, J=[skew(Tp) | -I]
+//                       -> 28-double block reduction (21 H + 6 b + err), deterministic last-block finalisation,
+//                       result published into mapped pinned host memory
 //   error_kernel        fgi:355-378  sum e^T M e with frozen correspondences
 //   align()             pcl::Registration::align + fgi:225-240 + lsq:53-173 (LM loop, 6x6 LDLT on the host)
 //
@@ -49,29 +50,21 @@ struct CovArgs {
   float* new_xyz;    // [3 * num_trackable] (only with filter)
 };
 
-constexpr int kKnnGroup = 4;  // lanes cooperating on one k-NN query
-
-// k-NN of every point of the cloud in itself: ids and squared distances, sorted by (d2, id)
+// k-NN of every point of the cloud in itself, one warp per point: ids and squared distances sorted by (d2, id).
+// The query point itself is its own nearest neighbour (distance 0), as with the reference's kd-tree search.
 template <int K>
-__global__ void __launch_bounds__(128, 2)
+__global__ void __launch_bounds__(128)
 knn_kernel(GridView g, int n, int k, const float* __restrict__ xyz, uint32_t* __restrict__ nn_id, float* __restrict__ nn_d2) {
-  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
-  const int i = tid / kKnnGroup, gl = tid % kKnnGroup;
-  if (i >= n) return;  // group-uniform
-  const unsigned gmask = ((1u << kKnnGroup) - 1u) << ((threadIdx.x & 31) & ~(kKnnGroup - 1));
-  TopK<K> nn;
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (i >= n) return;  // warp-uniform
+  const int lane = threadIdx.x & 31;
   const int kk = min(k, K);
-  // the query point itself is its own nearest neighbour (distance 0), as with the reference's kd-tree search
-  grid_knn<K, kKnnGroup>(g, xyz[3 * (size_t)i], xyz[3 * (size_t)i + 1], xyz[3 * (size_t)i + 2], kk, 0xffffffffu, nn, gl, gmask);
-  grid_knn_merge<K, kKnnGroup>(nn, kk, gmask);
-  if (gl == 0) {
-#pragma unroll
-    for (int j = 0; j < K; j++) {
-      if (j < kk) {
-        nn_id[(size_t)i * K + j] = nn.id[j];
-        nn_d2[(size_t)i * K + j] = nn.d2[j];
-      }
-    }
+  float d2;
+  uint32_t id;
+  grid_knn_warp(g, xyz[3 * (size_t)i], xyz[3 * (size_t)i + 1], xyz[3 * (size_t)i + 2], kk, 0xffffffffu, d2, id);
+  if (lane < kk) {
+    nn_id[(size_t)i * K + lane] = id;
+    nn_d2[(size_t)i * K + lane] = d2;
   }
 }
 
@@ -272,34 +265,40 @@ struct LinArgs {
   unsigned long long seq;
 };
 
-constexpr int kLinGroup = 4;  // lanes cooperating on one source point's nearest-neighbour search
+// Correspondence search (fgi:242-272): one WARP per source point.  fp32 transform of the query, exact 1-NN in the
+// target grid, squared distance and thresholded index.
+__global__ void __launch_bounds__(128)
+correspond_kernel(GridView tgt, PoseD T, int begin, int end, double max_corr_sq, const float* __restrict__ src_xyz,
+                  int32_t* __restrict__ corr, float* __restrict__ sqd) {
+  const int i = begin + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  if (i >= end) return;  // warp-uniform
+  const float px = src_xyz[3 * (size_t)i], py = src_xyz[3 * (size_t)i + 1], pz = src_xyz[3 * (size_t)i + 2];
+  // ((r0*x + r1*y) + r2*z) + t in fp32 without contraction (fgi:260-262)
+  const float tx = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(T.Rf[0][0], px), __fmul_rn(T.Rf[0][1], py)), __fmul_rn(T.Rf[0][2], pz)), T.tf[0]);
+  const float ty = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(T.Rf[1][0], px), __fmul_rn(T.Rf[1][1], py)), __fmul_rn(T.Rf[1][2], pz)), T.tf[1]);
+  const float tz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(T.Rf[2][0], px), __fmul_rn(T.Rf[2][1], py)), __fmul_rn(T.Rf[2][2], pz)), T.tf[2]);
+  float d2;
+  uint32_t id;
+  grid_nn_warp(tgt, tx, ty, tz, d2, id);
+  if ((threadIdx.x & 31) == 0) {
+    sqd[i] = d2;
+    corr[i] = ((tgt.n > 0) && ((double)d2 < max_corr_sq)) ? (int32_t)id : -1;
+  }
+}
 
+// Mahalanobis + residual/Jacobian + normal-equation reduction (fgi:273-352): one THREAD per source point.
 __global__ void __launch_bounds__(kLinBlock, 1)
-linearize_kernel(GridView tgt, PoseD T, LinArgs a) {
-  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
-  const int i = a.begin + tid / kLinGroup, gl = tid % kLinGroup;
-  const unsigned gmask = ((1u << kLinGroup) - 1u) << ((threadIdx.x & 31) & ~(kLinGroup - 1));
+linearize_kernel(PoseD T, LinArgs a) {
+  const int i = a.begin + blockIdx.x * blockDim.x + threadIdx.x;
   double v[kRed];
 #pragma unroll
   for (int k = 0; k < kRed; k++) v[k] = 0.0;
 
   if (i < a.end) {
     const float px = a.src_xyz[3 * (size_t)i], py = a.src_xyz[3 * (size_t)i + 1], pz = a.src_xyz[3 * (size_t)i + 2];
-    // fp32 transform of the query (fgi:260-262): ((r0*x + r1*y) + r2*z) + t
-    const float tx = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(T.Rf[0][0], px), __fmul_rn(T.Rf[0][1], py)), __fmul_rn(T.Rf[0][2], pz)), T.tf[0]);
-    const float ty = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(T.Rf[1][0], px), __fmul_rn(T.Rf[1][1], py)), __fmul_rn(T.Rf[1][2], pz)), T.tf[1]);
-    const float tz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(T.Rf[2][0], px), __fmul_rn(T.Rf[2][1], py)), __fmul_rn(T.Rf[2][2], pz)), T.tf[2]);
-    TopK<1> nn;
-    grid_knn<1, kLinGroup>(tgt, tx, ty, tz, 1, 0xffffffffu, nn, gl, gmask);
-    grid_knn_merge<1, kLinGroup>(nn, 1, gmask);
-    const float d2 = nn.d2[0];
-    const bool matched = (tgt.n > 0) && ((double)d2 < a.max_corr_sq);
-    const int32_t j = matched ? (int32_t)nn.id[0] : -1;
-    if (gl == 0) {
-      a.sqd[i] = d2;
-      a.corr[i] = j;
-    }
-    if (matched && gl == 0) {
+    const int32_t j = a.corr[i];
+    const bool matched = j >= 0;
+    if (matched) {
       const double* ca = a.src_cov + 6 * (size_t)i;
       const double* cb = a.tgt_cov + 6 * (size_t)j;
       const double A[3][3] = {{ca[0], ca[1], ca[2]}, {ca[1], ca[3], ca[4]}, {ca[2], ca[4], ca[5]}};
@@ -685,7 +684,7 @@ int compute_covariances(gsicp_gicp* h, Cloud& c, bool with_filter, bool clamp) {
   if (int e = h->nn_d2.ensure((size_t)n * K * 4)) return e;
   uint32_t* nid = h->nn_id.as<uint32_t>();
   float* nd2 = h->nn_d2.as<float>();
-  const int kgrid = (int)(((size_t)n * kKnnGroup + 127) / 128);
+  const int kgrid = (int)(((size_t)n * 32 + 127) / 128);
   if (K == 10) {
     GSICP_LAUNCH(knn_kernel<10>, kgrid, 128, 0, h->stream, c.grid.view(), n, h->k, c.xyz.as<float>(), nid, nd2);
     GSICP_LAUNCH(covariance_kernel<10>, grid, 128, 0, h->stream, a, nid, nd2);
@@ -747,7 +746,7 @@ void shard_range(const gsicp_gicp* h, int n, int& begin, int& end) {
 
 int ensure_lin_buffers(gsicp_gicp* h) {
   const int n = h->src.n;
-  const int blocks = (int)(((size_t)n * kLinGroup + kLinBlock - 1) / kLinBlock) + 1;
+  const int blocks = (n + kLinBlock - 1) / kLinBlock + 1;
   if (int e = h->corr.ensure((size_t)(n + 1) * 4)) return e;
   if (int e = h->sqd.ensure((size_t)(n + 1) * 4)) return e;
   if (int e = h->mahal.ensure((size_t)(n + 1) * 6 * sizeof(double))) return e;
@@ -812,10 +811,15 @@ int run_linearize(gsicp_gicp* h, const Iso& x, double H[6][6], double b[6], doub
   a.host_out = direct ? (double*)h->d_map : nullptr;
   a.host_seq = direct ? (volatile unsigned long long*)(h->d_map + 28) : nullptr;
   a.seq = ++h->seq;
-  int blocks = (int)(((size_t)(end - begin) * kLinGroup + kLinBlock - 1) / kLinBlock);
+  int blocks = (end - begin + kLinBlock - 1) / kLinBlock;
   if (blocks < 1) blocks = 1;
   { ProfScope ps(kProfLinearize, h->stream);
-  GSICP_LAUNCH(linearize_kernel, blocks, kLinBlock, 0, h->stream, h->tgt.grid.view(), make_pose(x), a); }
+  if (end > begin) {
+    const int nn_blocks = (int)(((size_t)(end - begin) * 32 + 127) / 128);
+    GSICP_LAUNCH(correspond_kernel, nn_blocks, 128, 0, h->stream, h->tgt.grid.view(), make_pose(x), begin, end, a.max_corr_sq,
+                 a.src_xyz, a.corr, a.sqd);
+  }
+  GSICP_LAUNCH(linearize_kernel, blocks, kLinBlock, 0, h->stream, make_pose(x), a); }
   if (h->shard_count > 1 && h->reduce) {
     const int rc = h->reduce(h->reduce_user, h->red_out.as<double>(), kRed, (void*)h->stream);
     if (rc != 0) {

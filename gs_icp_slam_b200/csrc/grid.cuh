@@ -200,149 +200,234 @@ struct DeviceGrid {
 };
 
 // ---- query ------------------------------------------------------------------------------------
-// Sorted top-K list ordered by (d2, idx).  K is a compile-time capacity kept in registers.
-template <int K>
-struct TopK {
-  float d2[K];
-  uint32_t id[K];
-  __device__ __forceinline__ void init() {
-#pragma unroll
-    for (int i = 0; i < K; i++) {
-      d2[i] = FLT_MAX;
-      id[i] = 0xffffffffu;
-    }
-  }
-  __device__ __forceinline__ void push(float d, uint32_t idx) {
-    if (!(d < d2[K - 1] || (d == d2[K - 1] && idx < id[K - 1]))) return;
-    float cd = d;
-    uint32_t ci = idx;
-#pragma unroll
-    for (int i = 0; i < K; i++) {
-      const bool before = (cd < d2[i]) || (cd == d2[i] && ci < id[i]);
-      if (before) {
-        const float td = d2[i];
-        const uint32_t ti = id[i];
-        d2[i] = cd;
-        id[i] = ci;
-        cd = td;
-        ci = ti;
-      }
-    }
-  }
+// ------------------------------------------------------------------------------------------------
+// Warp-cooperative exact search: ONE WARP PER QUERY (all 32 lanes call with the same query).
+//
+// Ring r of cells around the query cell consists of (2r+1)^2 x-rows.  Consecutive x cells own consecutive point
+// ranges in `pts`, so a row on the shell of the ring is one contiguous range and an interior row contributes its two
+// end cells: at most 2 "slots" per row.  The lanes compute the slots' [begin,end) in parallel, a warp scan flattens
+// them, and the candidates are then read 32 at a time (coalesced float4 loads) regardless of how they are spread
+// over cells.  The ring loop stops when `want` candidates are closer than the nearest unsearched cell face — an exact
+// criterion; beyond kMaxRing rings (queries far outside the cloud) the warp scans the whole cloud linearly.
+// ------------------------------------------------------------------------------------------------
+struct RingCursor {  // warp-uniform description of the flattened candidate list of one group of 32 slots
+  uint32_t b, excl, total;  // per lane: slot begin and exclusive prefix of the slot lengths; total is uniform
 };
 
-// Exact k-nearest search of (qx,qy,qz) in the grid by a GROUP of G consecutive lanes (G = 1, 2, 4, 8 ...).
-//   kth     = number of neighbours that must be final (<= K);  exclude = original index to skip (0xffffffff: none)
-//   g       = lane's rank inside its group, gmask = shuffle mask of the group's lanes (all must call together)
-// The cells of ring r form (2r+1)^2 x-rows; the points of consecutive x cells are contiguous in `pts`, so a shell row is
-// ONE contiguous point range (two cell_start loads).  Rows are dealt round-robin to the lanes of the group, each lane keeps
-// its own sorted top-K, and the ring loop stops when the group has seen `want` candidates closer than the nearest
-// unsearched cell face — the same exact criterion as a single sorted list (a lane's list truncates only when it alone
-// holds K >= want such candidates).  Call grid_knn_merge afterwards to obtain the group's sorted top-kth in every lane.
-template <int K, int G>
-__device__ __forceinline__ void grid_knn(const GridView& g_, float qx, float qy, float qz, int kth, uint32_t exclude,
-                                         TopK<K>& best, int g = 0, unsigned gmask = 0xffffffffu) {
-  best.init();
-  if (g_.n <= 0) return;
-  const GridMeta m = *g_.meta;
-  const int3 c0 = grid_cell_of(m, qx, qy, qz);
-  const int want = min(kth, g_.n - (exclude != 0xffffffffu ? 1 : 0));
-  bool finished = (want <= 0);
-  auto scan_range = [&](uint32_t b, uint32_t e) {
-    for (uint32_t i = b; i < e; i++) {
-      const float4 p = g_.pts[i];
-      const uint32_t pid = __float_as_uint(p.w);
-      if (pid == exclude) continue;
-      best.push(dist2_nofma(p.x, p.y, p.z, qx, qy, qz), pid);
-    }
-  };
-  for (int r = 0; r <= kMaxRing && !finished; r++) {
-    const int x0 = max(c0.x - r, 0), x1 = min(c0.x + r, m.nx - 1);
-    const int y0 = max(c0.y - r, 0), y1 = min(c0.y + r, m.ny - 1);
-    const int z0 = max(c0.z - r, 0), z1 = min(c0.z + r, m.nz - 1);
-    int row = 0;
-    for (int z = z0; z <= z1; z++) {
-      for (int y = y0; y <= y1; y++, row++) {
-        if (G > 1 && (row % G) != g) continue;
-        const int base = (z * m.ny + y) * m.nx;
-        if (abs(z - c0.z) == r || abs(y - c0.y) == r) {  // row lies on the shell: cells x0..x1 are one point range
-          scan_range(g_.cell_start[base + x0], g_.cell_start[base + x1 + 1]);
-        } else {  // interior row: only the two end cells belong to ring r
-          if (c0.x - r >= 0) scan_range(g_.cell_start[base + c0.x - r], g_.cell_start[base + c0.x - r + 1]);
-          if (c0.x + r <= m.nx - 1) scan_range(g_.cell_start[base + c0.x + r], g_.cell_start[base + c0.x + r + 1]);
+__device__ __forceinline__ RingCursor ring_slots(const GridView& g, const GridMeta& m, int3 c0, int r, int slot0, int lane) {
+  const int side = 2 * r + 1;
+  const int s = slot0 + lane;
+  uint32_t b = 0, e = 0;
+  if (s < 2 * side * side) {
+    const int row = s >> 1, half = s & 1;
+    const int dz = row / side - r, dy = row % side - r;
+    const int z = c0.z + dz, y = c0.y + dy;
+    if (z >= 0 && z < m.nz && y >= 0 && y < m.ny) {
+      const int base = (z * m.ny + y) * m.nx;
+      if (abs(dz) == r || abs(dy) == r) {
+        if (half == 0) {
+          b = g.cell_start[base + max(c0.x - r, 0)];
+          e = g.cell_start[base + min(c0.x + r, m.nx - 1) + 1];
+        }
+      } else {
+        const int x = half == 0 ? c0.x - r : c0.x + r;
+        if (x >= 0 && x < m.nx) {
+          b = g.cell_start[base + x];
+          e = g.cell_start[base + x + 1];
         }
       }
     }
-    if (x0 == 0 && y0 == 0 && z0 == 0 && x1 == m.nx - 1 && y1 == m.ny - 1 && z1 == m.nz - 1) {
-      finished = true;  // the whole grid has been searched
-      break;
+  }
+  const uint32_t len = e - b;
+  uint32_t incl = len;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  RingCursor c;
+  c.b = b;
+  c.excl = incl - len;
+  c.total = __shfl_sync(0xffffffffu, incl, 31);
+  return c;
+}
+
+// index into g.pts of flattened element t (t < total), for every lane independently
+__device__ __forceinline__ uint32_t ring_element(const RingCursor& c, uint32_t t) {
+  int lo = 0;  // largest slot k with excl[k] <= t
+#pragma unroll
+  for (int step = 16; step >= 1; step >>= 1) {
+    const int probe = lo + step;
+    const uint32_t v = __shfl_sync(0xffffffffu, c.excl, probe & 31);
+    if (probe < 32 && v <= t) lo = probe;
+  }
+  const uint32_t sb = __shfl_sync(0xffffffffu, c.b, lo);
+  const uint32_t se = __shfl_sync(0xffffffffu, c.excl, lo);
+  return sb + (t - se);
+}
+
+__device__ __forceinline__ float ring_bound(const GridMeta& m, int3 c0, int r, float qx, float qy, float qz, bool& all) {
+  all = (c0.x - r <= 0 && c0.y - r <= 0 && c0.z - r <= 0 && c0.x + r >= m.nx - 1 && c0.y + r >= m.ny - 1 && c0.z + r >= m.nz - 1);
+  float bound = FLT_MAX;
+  if (c0.x - r > 0) bound = fminf(bound, qx - (m.ox + (c0.x - r) * m.cell));
+  if (c0.x + r < m.nx - 1) bound = fminf(bound, (m.ox + (c0.x + r + 1) * m.cell) - qx);
+  if (c0.y - r > 0) bound = fminf(bound, qy - (m.oy + (c0.y - r) * m.cell));
+  if (c0.y + r < m.ny - 1) bound = fminf(bound, (m.oy + (c0.y + r + 1) * m.cell) - qy);
+  if (c0.z - r > 0) bound = fminf(bound, qz - (m.oz + (c0.z - r) * m.cell));
+  if (c0.z + r < m.nz - 1) bound = fminf(bound, (m.oz + (c0.z + r + 1) * m.cell) - qz);
+  // conservative: shrink by the fp32 error of the face coordinates and of the distances
+  const float safe = fmaxf(bound, 0.f) * (1.0f - 1e-5f) - 1e-6f * m.cell;
+  return safe > 0.f ? safe * safe * (1.0f - 1e-5f) : -1.f;  // squared; -1: no conclusion possible yet
+}
+
+// k-NN, k <= 32.  On return lane i < kth holds the i-th nearest (d2, id), ordered by (d2, id); the other lanes
+// hold (FLT_MAX, 0xffffffff).
+__device__ __forceinline__ void grid_knn_warp(const GridView& g, float qx, float qy, float qz, int kth, uint32_t exclude,
+                                              float& my_d2, uint32_t& my_id) {
+  const int lane = threadIdx.x & 31;
+  my_d2 = FLT_MAX;
+  my_id = 0xffffffffu;
+  if (g.n <= 0 || kth <= 0) return;
+  const GridMeta m = *g.meta;
+  const int3 c0 = grid_cell_of(m, qx, qy, qz);
+  const int want = min(kth, g.n - (exclude != 0xffffffffu ? 1 : 0));
+  if (want <= 0) return;
+
+  auto offer = [&](float d, uint32_t id, bool valid) {  // every lane offers one candidate
+    float thr_d = __shfl_sync(0xffffffffu, my_d2, kth - 1);
+    uint32_t thr_i = __shfl_sync(0xffffffffu, my_id, kth - 1);
+    bool cand = valid && (d < thr_d || (d == thr_d && id < thr_i));
+    unsigned mask = __ballot_sync(0xffffffffu, cand);
+    while (mask) {
+      const int src = __ffs(mask) - 1;
+      const float cd = __shfl_sync(0xffffffffu, d, src);
+      const uint32_t ci = __shfl_sync(0xffffffffu, id, src);
+      // sorted insertion across the lanes: entries ranking after the candidate shift up by one lane
+      const bool greater = (my_d2 > cd) || (my_d2 == cd && my_id > ci);
+      const float up_d = __shfl_up_sync(0xffffffffu, my_d2, 1);
+      const uint32_t up_i = __shfl_up_sync(0xffffffffu, my_id, 1);
+      const bool prev_greater = (__shfl_up_sync(0xffffffffu, (int)greater, 1) != 0) && lane > 0;
+      if (greater) {
+        my_d2 = prev_greater ? up_d : cd;
+        my_id = prev_greater ? up_i : ci;
+      }
+      if (lane >= kth) {
+        my_d2 = FLT_MAX;
+        my_id = 0xffffffffu;
+      }
+      thr_d = __shfl_sync(0xffffffffu, my_d2, kth - 1);
+      thr_i = __shfl_sync(0xffffffffu, my_id, kth - 1);
+      cand = cand && (lane != src) && (d < thr_d || (d == thr_d && id < thr_i));
+      mask = __ballot_sync(0xffffffffu, cand);
     }
-    // distance below which no unsearched point can exist: nearest face of the searched cube that has cells beyond it
-    float bound = FLT_MAX;
-    if (c0.x - r > 0) bound = fminf(bound, qx - (m.ox + (c0.x - r) * m.cell));
-    if (c0.x + r < m.nx - 1) bound = fminf(bound, (m.ox + (c0.x + r + 1) * m.cell) - qx);
-    if (c0.y - r > 0) bound = fminf(bound, qy - (m.oy + (c0.y - r) * m.cell));
-    if (c0.y + r < m.ny - 1) bound = fminf(bound, (m.oy + (c0.y + r + 1) * m.cell) - qy);
-    if (c0.z - r > 0) bound = fminf(bound, qz - (m.oz + (c0.z - r) * m.cell));
-    if (c0.z + r < m.nz - 1) bound = fminf(bound, (m.oz + (c0.z + r + 1) * m.cell) - qz);
-    // conservative: shrink by the fp32 error of the face coordinates and of the distances
-    const float safe = fmaxf(bound, 0.f) * (1.0f - 1e-5f) - 1e-6f * m.cell;
-    if (safe > 0.f) {
-      const float lim = safe * safe * (1.0f - 1e-5f);
-      int cnt = 0;
-#pragma unroll
-      for (int i = 0; i < K; i++) cnt += (best.d2[i] < lim) ? 1 : 0;
-#pragma unroll
-      for (int o = 1; o < G; o <<= 1) cnt += __shfl_xor_sync(gmask, cnt, o);
+  };
+
+  bool finished = false;
+  for (int r = 0; r <= kMaxRing && !finished; r++) {
+    const int nslots = 2 * (2 * r + 1) * (2 * r + 1);
+    for (int s0 = 0; s0 < nslots; s0 += 32) {
+      const RingCursor c = ring_slots(g, m, c0, r, s0, lane);
+      for (uint32_t t0 = 0; t0 < c.total; t0 += 32) {
+        const uint32_t t = t0 + lane;
+        const bool valid = t < c.total;
+        const uint32_t idx = ring_element(c, valid ? t : 0);
+        float d = FLT_MAX;
+        uint32_t id = 0xffffffffu;
+        if (valid) {
+          const float4 p = g.pts[idx];
+          id = __float_as_uint(p.w);
+          d = dist2_nofma(p.x, p.y, p.z, qx, qy, qz);
+        }
+        offer(d, id, valid && id != exclude);
+      }
+    }
+    bool all;
+    const float lim = ring_bound(m, c0, r, qx, qy, qz, all);
+    if (all) {
+      finished = true;
+    } else if (lim > 0.f) {
+      const int cnt = __popc(__ballot_sync(0xffffffffu, lane < kth && my_d2 < lim));
       if (cnt >= want) finished = true;
     }
   }
-  if (!finished) {  // far outside the occupied cells: exact linear scan, interleaved over the group
-    best.init();
-    for (int i = g; i < g_.n; i += G) {
-      const float4 p = g_.pts[i];
-      const uint32_t pid = __float_as_uint(p.w);
-      if (pid == exclude) continue;
-      best.push(dist2_nofma(p.x, p.y, p.z, qx, qy, qz), pid);
+  if (!finished) {  // far outside the occupied cells: exact linear scan of the whole cloud
+    my_d2 = FLT_MAX;
+    my_id = 0xffffffffu;
+    for (int base = 0; base < g.n; base += 32) {
+      const int i = base + lane;
+      float d = FLT_MAX;
+      uint32_t id = 0xffffffffu;
+      if (i < g.n) {
+        const float4 p = g.pts[i];
+        id = __float_as_uint(p.w);
+        d = dist2_nofma(p.x, p.y, p.z, qx, qy, qz);
+      }
+      offer(d, id, i < g.n && id != exclude);
     }
   }
 }
 
-// Merge the G per-lane lists of a group: afterwards every lane of the group holds the group's sorted top-`kth`
-// (entries beyond kth are unspecified).  G = 1: no-op.
-template <int K, int G>
-__device__ __forceinline__ void grid_knn_merge(TopK<K>& best, int kth, unsigned gmask) {
-  if (G == 1) return;
-  TopK<K> out;
-  out.init();
+// Nearest neighbour (k = 1): every lane keeps the best of the candidates it read, one argmin reduction per ring.
+// Returns (d2, id) of the nearest point in all lanes ((FLT_MAX, 0xffffffff) for an empty cloud).
+__device__ __forceinline__ void grid_nn_warp(const GridView& g, float qx, float qy, float qz, float& out_d2, uint32_t& out_id) {
+  const int lane = threadIdx.x & 31;
+  float bd = FLT_MAX;
+  uint32_t bi = 0xffffffffu;
+  out_d2 = bd;
+  out_id = bi;
+  if (g.n <= 0) return;
+  const GridMeta m = *g.meta;
+  const int3 c0 = grid_cell_of(m, qx, qy, qz);
+  auto take = [&](float d, uint32_t id) {
+    if (d < bd || (d == bd && id < bi)) {
+      bd = d;
+      bi = id;
+    }
+  };
+  auto reduce = [&]() {
+    float d = bd;
+    uint32_t i = bi;
 #pragma unroll
-  for (int t = 0; t < K; t++) {
-    if (t < kth) {
-      float wd = best.d2[0];
-      uint32_t wi = best.id[0];
-#pragma unroll
-      for (int o = 1; o < G; o <<= 1) {
-        const float od = __shfl_xor_sync(gmask, wd, o);
-        const uint32_t oi = __shfl_xor_sync(gmask, wi, o);
-        if (od < wd || (od == wd && oi < wi)) {
-          wd = od;
-          wi = oi;
-        }
-      }
-      out.d2[t] = wd;
-      out.id[t] = wi;
-      if (best.id[0] == wi && best.d2[0] == wd && wi != 0xffffffffu) {  // this lane owned the winner: pop it
-#pragma unroll
-        for (int i = 0; i < K - 1; i++) {
-          best.d2[i] = best.d2[i + 1];
-          best.id[i] = best.id[i + 1];
-        }
-        best.d2[K - 1] = FLT_MAX;
-        best.id[K - 1] = 0xffffffffu;
+    for (int o = 16; o >= 1; o >>= 1) {
+      const float od = __shfl_xor_sync(0xffffffffu, d, o);
+      const uint32_t oi = __shfl_xor_sync(0xffffffffu, i, o);
+      if (od < d || (od == d && oi < i)) {
+        d = od;
+        i = oi;
       }
     }
+    out_d2 = d;
+    out_id = i;
+  };
+  bool finished = false;
+  for (int r = 0; r <= kMaxRing && !finished; r++) {
+    const int nslots = 2 * (2 * r + 1) * (2 * r + 1);
+    for (int s0 = 0; s0 < nslots; s0 += 32) {
+      const RingCursor c = ring_slots(g, m, c0, r, s0, lane);
+      for (uint32_t t0 = 0; t0 < c.total; t0 += 32) {
+        const uint32_t t = t0 + lane;
+        const bool valid = t < c.total;
+        const uint32_t idx = ring_element(c, valid ? t : 0);
+        if (valid) {
+          const float4 p = g.pts[idx];
+          take(dist2_nofma(p.x, p.y, p.z, qx, qy, qz), __float_as_uint(p.w));
+        }
+      }
+    }
+    bool all;
+    const float lim = ring_bound(m, c0, r, qx, qy, qz, all);
+    reduce();
+    if (all || (lim > 0.f && out_d2 < lim)) finished = true;
   }
-  best = out;
+  if (!finished) {
+    bd = FLT_MAX;
+    bi = 0xffffffffu;
+    for (int i = lane; i < g.n; i += 32) {
+      const float4 p = g.pts[i];
+      take(dist2_nofma(p.x, p.y, p.z, qx, qy, qz), __float_as_uint(p.w));
+    }
+    reduce();
+  }
 }
 
 }  // namespace gsicp

@@ -9,18 +9,16 @@
 
 namespace gsicp {
 
-constexpr int kD2Group = 4;  // lanes cooperating on one query
-
+// one warp per point: exact 3-NN excluding the point itself
 __global__ void __launch_bounds__(128)
 dist2_kernel(GridView g, const float* __restrict__ xyz, float* __restrict__ out) {
-  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
-  const int i = tid / kD2Group, gl = tid % kD2Group;
-  if (i >= g.n) return;  // group-uniform
-  const unsigned gmask = ((1u << kD2Group) - 1u) << ((threadIdx.x & 31) & ~(kD2Group - 1));
-  TopK<3> best;
-  grid_knn<3, kD2Group>(g, xyz[3 * (size_t)i], xyz[3 * (size_t)i + 1], xyz[3 * (size_t)i + 2], 3, (uint32_t)i, best, gl, gmask);
-  grid_knn_merge<3, kD2Group>(best, 3, gmask);
-  if (gl == 0) out[i] = (best.d2[0] + best.d2[1] + best.d2[2]) / 3.0f;
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (i >= g.n) return;  // warp-uniform
+  float d2;
+  uint32_t id;
+  grid_knn_warp(g, xyz[3 * (size_t)i], xyz[3 * (size_t)i + 1], xyz[3 * (size_t)i + 2], 3, (uint32_t)i, d2, id);
+  const float a = __shfl_sync(0xffffffffu, d2, 0), b = __shfl_sync(0xffffffffu, d2, 1), c = __shfl_sync(0xffffffffu, d2, 2);
+  if ((threadIdx.x & 31) == 0) out[i] = (a + b + c) / 3.0f;
 }
 
 static DeviceGrid g_dist2_grid;
@@ -40,7 +38,7 @@ extern "C" int gsicp_dist2(int P, const float* d_points, float* d_out, void* str
   std::lock_guard<std::mutex> lock(g_dist2_mu);
   ProfScope ps(kProfDist2, stream);
   if (int e = g_dist2_grid.build(d_points, P, stream)) return e;
-  GSICP_LAUNCH(dist2_kernel, (int)(((size_t)P * kD2Group + 127) / 128), 128, 0, stream, g_dist2_grid.view(), d_points, d_out);
+  GSICP_LAUNCH(dist2_kernel, (int)(((size_t)P * 32 + 127) / 128), 128, 0, stream, g_dist2_grid.view(), d_points, d_out);
   GSICP_CUDA(cudaGetLastError());
   return GSICP_OK;
 }

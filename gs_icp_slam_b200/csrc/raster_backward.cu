@@ -27,14 +27,15 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 // work[P][8] = { dconic_xx, dconic_xy, dconic_yy, dcov_zx, dcov_yz, ddepth, -, - }
 template <bool kCull>
-__global__ void __launch_bounds__(kTilePixels, 3)
-render_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H,
+__global__ void __launch_bounds__(kTilePixels, 4)
+render_backward_kernel(const uint32_t* __restrict__ tile_order, const uint2* __restrict__ ranges,
+                       const uint32_t* __restrict__ point_list, int W, int H,
                        int tiles_x, const float* __restrict__ bg, const Splat* __restrict__ splats,
                        const float* __restrict__ final_T, const uint32_t* __restrict__ n_contrib,
                        const float* __restrict__ dL_dpix_color, const float* __restrict__ dL_dpix_depth,
                        float* __restrict__ dL_dmean2D, float* __restrict__ dL_dcolors, float* __restrict__ dL_dopacity,
                        float* __restrict__ work, int shard_count, int shard_index) {
-  const int tile = blockIdx.x;
+  const int tile = (int)tile_order[blockIdx.x];
   if (shard_count > 1 && (tile % shard_count) != shard_index) return;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int tile_x = tile % tiles_x, tile_y = tile / tiles_x;
@@ -511,11 +512,11 @@ extern "C" int gsicp_raster_backward(const gsicp_raster_args* args, int num_rend
   if (num_rendered > 0) {
     ProfScope ps(kProfRenderBwd, stream);
     if (g_render_cull) {
-      GSICP_LAUNCH(render_backward_kernel<true>, tiles, kTilePixels, 0, stream, img.ranges, bin.point_list, W, H, tiles_x,
+      GSICP_LAUNCH(render_backward_kernel<true>, tiles, kTilePixels, 0, stream, img.tile_order, img.ranges, bin.point_list, W, H, tiles_x,
                    args->d_background, geom.splats, img.final_T, img.n_contrib, d_dL_dout_color, d_dL_dout_depth,
                    d_dL_dmeans2D, d_dL_dcolors, d_dL_dopacity, work, shard_count, shard_index);
     } else {
-      GSICP_LAUNCH(render_backward_kernel<false>, tiles, kTilePixels, 0, stream, img.ranges, bin.point_list, W, H, tiles_x,
+      GSICP_LAUNCH(render_backward_kernel<false>, tiles, kTilePixels, 0, stream, img.tile_order, img.ranges, bin.point_list, W, H, tiles_x,
                    args->d_background, geom.splats, img.final_T, img.n_contrib, d_dL_dout_color, d_dL_dout_depth,
                    d_dL_dmeans2D, d_dL_dcolors, d_dL_dopacity, work, shard_count, shard_index);
     }

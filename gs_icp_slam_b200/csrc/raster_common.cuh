@@ -241,12 +241,14 @@ struct ImgState {       // kept for backward: 8 B / pixel + 8 B / tile
   float* final_T;       // [N] transmittance after the last blended Gaussian (T == T_d)
   uint32_t* n_contrib;  // [N] 1-based list position of the last blended Gaussian
   uint2* ranges;        // [tiles] [begin,end) into point_list
-  static size_t bytes(size_t N, size_t tiles) { return 3 * 128 + N * 8 + tiles * sizeof(uint2); }
+  uint32_t* tile_order; // [tiles] tile ids by decreasing instance count (launch order of the render CTAs)
+  static size_t bytes(size_t N, size_t tiles) { return 4 * 128 + N * 8 + tiles * (sizeof(uint2) + 4); }
   static ImgState from(char* p, size_t N, size_t tiles) {
     ImgState s;
     s.final_T = carve<float>(p, N);
     s.n_contrib = carve<uint32_t>(p, N);
     s.ranges = carve<uint2>(p, tiles);
+    s.tile_order = carve<uint32_t>(p, tiles);
     return s;
   }
 };

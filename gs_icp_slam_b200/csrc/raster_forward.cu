@@ -195,6 +195,32 @@ __global__ void tile_ranges_kernel(int R, const KeyT* __restrict__ keys, uint2* 
   if (i == R - 1) ranges[cur].y = R;
 }
 
+// Launch order of the render CTAs: tiles by decreasing instance count (bucketed by sqrt(count), one CTA).  The
+// hardware dispatches CTAs in index order, so the longest tiles start first and the short ones fill the tail
+// (longest-processing-time-first), instead of a long tile starting last and leaving the other SMs idle.
+__global__ void __launch_bounds__(1024) tile_order_kernel(int tiles, const uint2* __restrict__ ranges, uint32_t* __restrict__ order) {
+  __shared__ uint32_t hist[64], start[64];
+  if (threadIdx.x < 64) hist[threadIdx.x] = 0;
+  __syncthreads();
+  for (int t = threadIdx.x; t < tiles; t += blockDim.x) {
+    const uint32_t len = ranges[t].y - ranges[t].x;
+    atomicAdd(&hist[min(63, (int)sqrtf((float)len))], 1u);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t acc = 0;
+    for (int b = 63; b >= 0; b--) {
+      start[b] = acc;
+      acc += hist[b];
+    }
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < tiles; t += blockDim.x) {
+    const uint32_t len = ranges[t].y - ranges[t].x;
+    order[atomicAdd(&start[min(63, (int)sqrtf((float)len))], 1u)] = (uint32_t)t;
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // render forward: one CTA per 16x16 tile, each warp owns an 8x4 sub-tile.
 //
@@ -208,11 +234,12 @@ __global__ void tile_ranges_kernel(int R, const KeyT* __restrict__ keys, uint2* 
 // ------------------------------------------------------------------------------------------
 template <bool kCull>
 __global__ void __launch_bounds__(kTilePixels)
-render_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H,
+render_forward_kernel(const uint32_t* __restrict__ tile_order, const uint2* __restrict__ ranges,
+                      const uint32_t* __restrict__ point_list, int W, int H,
                       int tiles_x, const Splat* __restrict__ splats, const float* __restrict__ bg,
                       float* __restrict__ out_color, float* __restrict__ out_depth, float* __restrict__ final_T,
                       uint32_t* __restrict__ n_contrib, int shard_count, int shard_index) {
-  const int tile = blockIdx.x;
+  const int tile = (int)tile_order[blockIdx.x];
   if (shard_count > 1 && (tile % shard_count) != shard_index) return;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int tile_x = tile % tiles_x, tile_y = tile / tiles_x;
@@ -516,13 +543,14 @@ extern "C" int gsicp_raster_forward(const gsicp_raster_args* args, float* d_out_
   }
 
   if (P > 0) {
+    GSICP_LAUNCH(tile_order_kernel, 1, 1024, 0, stream, tiles, img.ranges, img.tile_order);
     ProfScope ps(kProfRenderFwd, stream);
     if (g_render_cull) {
-      GSICP_LAUNCH(render_forward_kernel<true>, tiles, kTilePixels, 0, stream, img.ranges, bin.point_list, W, H, tiles_x,
+      GSICP_LAUNCH(render_forward_kernel<true>, tiles, kTilePixels, 0, stream, img.tile_order, img.ranges, bin.point_list, W, H, tiles_x,
                    geom.splats, args->d_background, d_out_color, d_out_depth, img.final_T, img.n_contrib, shard_count,
                    shard_index);
     } else {
-      GSICP_LAUNCH(render_forward_kernel<false>, tiles, kTilePixels, 0, stream, img.ranges, bin.point_list, W, H, tiles_x,
+      GSICP_LAUNCH(render_forward_kernel<false>, tiles, kTilePixels, 0, stream, img.tile_order, img.ranges, bin.point_list, W, H, tiles_x,
                    geom.splats, args->d_background, d_out_color, d_out_depth, img.final_T, img.n_contrib, shard_count,
                    shard_index);
     }

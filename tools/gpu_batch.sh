@@ -9,6 +9,7 @@ step 200 python -X faulthandler tools/host_breakdown2.py > gpurun_out/host_break
 step 300 python bench.py --steps 30 --warmup 3 --overlap 0 --no-cpu-baseline > gpurun_out/bench_seq.log 2>&1
 step 400 python bench.py --steps 30 --warmup 3 --overlap 1 > gpurun_out/bench_ovl.log 2>&1
 step 300 python bench.py --impl reference --steps 10 --warmup 2 > gpurun_out/bench_ref.log 2>&1
+step 200 python tools/gpu_diag_raster.py > gpurun_out/diag_raster.log 2>&1; grep -E "mismatch|time ms" gpurun_out/diag_raster.log | tail -12
 grep -h "step rc" gpurun_out/*.log 2>/dev/null
 python - <<PY
 import json
