@@ -25,7 +25,14 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-// work[P][8] = { dconic_xx, dconic_xy, dconic_yy, dcov_zx, dcov_yz, ddepth, -, - }
+// moments[P][12]: per Gaussian, summed over every pixel it was blended into (one fp32 RED per lane-owned sum):
+//   [0..2] sum w dL/dpix_rgb        (= dL/dcolour)             w = alpha * T
+//   [3]    sum v                    (= dL/ddepth)              v = w * dL/dpix_depth
+//   [4]    sum t                    (= dL/dopacity)            t = G (dL/dalpha + dL/dalpha_d)
+//   [5..9] sum u dx, u dy, u dx^2, u dx dy, u dy^2             u = opacity * t
+//   [10,11] sum v dx, v dy
+// The reference's 12 per-pair gradient expressions (backward.cu:575-654) are linear in these moments with
+// per-Gaussian coefficients; gaussian_backward_kernel forms them once per Gaussian.
 template <bool kCull>
 __global__ void __launch_bounds__(kTilePixels, 4)
 render_backward_kernel(const uint32_t* __restrict__ tile_order, const uint2* __restrict__ ranges,
@@ -33,8 +40,7 @@ render_backward_kernel(const uint32_t* __restrict__ tile_order, const uint2* __r
                        int tiles_x, const float* __restrict__ bg, const Splat* __restrict__ splats,
                        const float* __restrict__ final_T, const uint32_t* __restrict__ n_contrib,
                        const float* __restrict__ dL_dpix_color, const float* __restrict__ dL_dpix_depth,
-                       float* __restrict__ dL_dmean2D, float* __restrict__ dL_dcolors, float* __restrict__ dL_dopacity,
-                       float* __restrict__ work, int shard_count, int shard_index) {
+                       float* __restrict__ moments, int shard_count, int shard_index) {
   const int tile = (int)tile_order[blockIdx.x];
   if (shard_count > 1 && (tile % shard_count) != shard_index) return;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -45,10 +51,9 @@ render_backward_kernel(const uint32_t* __restrict__ tile_order, const uint2* __r
   const float pxf = (float)px, pyf = (float)py;
   const int pix = py * W + px;
 
-  __shared__ float4 sA[kTilePixels], sB[kTilePixels], sC[kTilePixels];
-  __shared__ uint32_t sId[kTilePixels];
-  __shared__ float sAcc[kTilePixels * kG];
-  __shared__ uint32_t sTouched[kTilePixels / 32];
+  // double-buffered staging of 256 instances: one barrier per batch, loads of batch k+1 overlap the math of batch k
+  __shared__ float4 sA[2][kTilePixels], sB[2][kTilePixels], sC[2][kTilePixels];
+  __shared__ uint32_t sId[2][kTilePixels];
 
   const uint2 range = ranges[tile];
   const int total = (int)(range.y - range.x);
@@ -71,160 +76,128 @@ render_backward_kernel(const uint32_t* __restrict__ tile_order, const uint2* __r
   }
   const float bg_dot_dpixel = bg[0] * dpr + bg[1] * dpg + bg[2] * dpb;
   const float bg_dot_ddepth = 15.f * dpd;
+  const float bg_term = T_final * (bg_dot_dpixel + bg_dot_ddepth);  // background share of dL/dalpha + dL/dalpha_d
 
   float last_alpha = 0.f, last_r = 0.f, last_g = 0.f, last_b = 0.f, last_depth = 0.f;
   float acc_r = 0.f, acc_g = 0.f, acc_b = 0.f, acc_d = 0.f;
-  const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
   // lane roles of the recursive-halving reduction (see below)
   const bool b16 = lane & 16, b8 = lane & 8, b4 = lane & 4, b2 = lane & 2;
   const int red_var = (b16 ? 6 : 0) + (b8 ? 3 : 0) + (b4 ? 2 : (b2 ? 1 : 0));
   const bool red_valid = !(b4 && b2) && !(lane & 1);
 
   // Back to front: batch `base` covers list positions [total-base-n, total-base), staged reversed
-  // (sX[k] = position total-base-1-k) like backward.cu:519-531.
-  for (int base = 0; base < total; base += kTilePixels) {
+  // (slot k = position total-base-1-k) like backward.cu:519-531.
+  auto stage = [&](int base, int buf) {
     const int n = min(kTilePixels, total - base);
-    __syncthreads();
     if (tid < n) {
       const uint32_t g = point_list[range.y - 1 - base - tid];
       const Splat* sp = splats + g;
-      sId[tid] = g;
-      sA[tid] = __ldg(&sp->a);
-      sB[tid] = __ldg(&sp->b);
-      sC[tid] = __ldg(&sp->c);
+      sId[buf][tid] = g;
+      sA[buf][tid] = __ldg(&sp->a);
+      sB[buf][tid] = __ldg(&sp->b);
+      sC[buf][tid] = __ldg(&sp->c);
     }
-#pragma unroll
-    for (int k = 0; k < kG; k++) sAcc[k * kTilePixels + tid] = 0.f;
-    if (tid < kTilePixels / 32) sTouched[tid] = 0u;
-    __syncthreads();
+  };
+  if (total > 0) stage(0, 0);
 
-    // position (1-based contributor id) of sX[k] is total - base - k
-    const int first_pos = total - base;  // contributor id of k = 0
-    if (first_pos - (n - 1) <= warp_last) {
-      for (int c0 = 0; c0 < n; c0 += 32) {
-        if (first_pos - c0 - 31 > warp_last && c0 + 32 <= n) continue;  // whole chunk behind the last contributor
-        uint32_t mask;
-        {
-          const int j = c0 + lane;
-          bool hit = (j < n) && (first_pos - j <= warp_last);
-          if (kCull) hit = hit && subtile_hit(sA[j < n ? j : 0], sB[j < n ? j : 0], (float)wx0, (float)wy0, 7.f, 3.f);
-          mask = __ballot_sync(0xffffffffu, hit);
+  for (int base = 0, buf = 0; base < total; base += kTilePixels, buf ^= 1) {
+    const int n = min(kTilePixels, total - base);
+    __syncthreads();  // batch `base` is staged; every warp has finished reading the other buffer
+    if (base + kTilePixels < total) stage(base + kTilePixels, buf ^ 1);
+
+    const int first_pos = total - base;  // 1-based contributor id of slot 0
+    if (first_pos - (n - 1) > warp_last) continue;  // the whole batch lies behind this warp's last contributor
+    for (int c0 = 0; c0 < n; c0 += 32) {
+      if (first_pos - c0 - 31 > warp_last && c0 + 32 <= n) continue;  // whole chunk behind the last contributor
+      uint32_t mask;
+      {
+        const int j = c0 + lane;
+        bool hit = (j < n) && (first_pos - j <= warp_last);
+        if (kCull) hit = hit && subtile_hit(sA[buf][j < n ? j : 0], sB[buf][j < n ? j : 0], (float)wx0, (float)wy0, 7.f, 3.f);
+        mask = __ballot_sync(0xffffffffu, hit);
+      }
+      while (mask) {
+        const int bit = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const int j = c0 + bit;
+        const int contributor = first_pos - j;  // 1-based; reference compares (contributor-1) >= last (backward.cu:540-542)
+        const float4 a = sA[buf][j], b = sB[buf][j];
+        const float dx = a.x - pxf, dy = a.y - pyf;
+        const float power = -0.5f * (a.z * dx * dx + b.x * dy * dy) - a.w * dx * dy;
+        const float G = expf(power);
+        const float alpha = fminf(0.99f, b.y * G);
+        const bool active = inside && (contributor <= last_contributor) && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
+
+        const unsigned act = __ballot_sync(0xffffffffu, active);
+        if (!act) continue;  // no pixel of this sub-tile blended the instance: skip the gradient arithmetic
+
+        float g[kG];
+#pragma unroll
+        for (int k = 0; k < kG; k++) g[k] = 0.f;
+        if (active) {
+          const float4 c = sC[buf][j];
+          const float inv = __frcp_rn(1.f - alpha);  // correctly rounded reciprocal, shared by the three divisions
+          T = T * inv;                               // transmittance in front of this Gaussian (backward.cu:555)
+          const float w = alpha * T;                 // d(pixel channel)/d(colour), also d(pixel depth)/d(depth)
+
+          // colour and depth blended behind this Gaussian (backward.cu:563-576, 617-620)
+          acc_r = last_alpha * last_r + (1.f - last_alpha) * acc_r;
+          acc_g = last_alpha * last_g + (1.f - last_alpha) * acc_g;
+          acc_b = last_alpha * last_b + (1.f - last_alpha) * acc_b;
+          acc_d = last_alpha * last_depth + (1.f - last_alpha) * acc_d;
+          const float czx = b.z, cyz = b.w;
+          const float depth = c.w - (czx * a.z + cyz * a.w) * dx - (czx * a.w + cyz * b.x) * dy;
+          last_r = c.x; last_g = c.y; last_b = c.z; last_depth = depth;
+          last_alpha = alpha;
+          // dL/dalpha (colour) + dL/dalpha_d (depth; same alpha and transmittance, T_d == T bit for bit)
+          const float dsum = ((c.x - acc_r) * dpr + (c.y - acc_g) * dpg + (c.z - acc_b) * dpb + (depth - acc_d) * dpd) * T -
+                             bg_term * inv;
+          const float t = G * dsum;
+          const float u = b.y * t;
+          const float v = w * dpd;
+          const float udx = u * dx, udy = u * dy;
+          g[0] = w * dpr; g[1] = w * dpg; g[2] = w * dpb;
+          g[3] = v;
+          g[4] = t;
+          g[5] = udx;
+          g[6] = udy;
+          g[7] = udx * dx;
+          g[8] = udx * dy;
+          g[9] = udy * dy;
+          g[10] = v * dx;
+          g[11] = v * dy;
         }
-        while (mask) {
-          const int bit = __ffs(mask) - 1;
-          mask &= mask - 1;
-          const int j = c0 + bit;
-          const int contributor = first_pos - j;  // 1-based; reference compares (contributor-1) >= last (backward.cu:540-542)
-          const float4 a = sA[j], b = sB[j];
-          const float dx = a.x - pxf, dy = a.y - pyf;
-          const float power = -0.5f * (a.z * dx * dx + b.x * dy * dy) - a.w * dx * dy;
-          const float G = expf(power);
-          const float alpha = fminf(0.99f, b.y * G);
-          const bool active = inside && (contributor <= last_contributor) && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
-
-          const unsigned act = __ballot_sync(0xffffffffu, active);
-          if (!act) continue;  // no pixel of this sub-tile blended the instance: skip the gradient arithmetic
-
-          float g[kG];
-#pragma unroll
-          for (int k = 0; k < kG; k++) g[k] = 0.f;
+        float* dst = moments + (size_t)sId[buf][j] * kG;
+        if (__popc(act) <= 2) {
+          // one or two pixels of the sub-tile see this Gaussian (ellipse edge): add them directly
           if (active) {
-            const float4 c = sC[j];
-            T = T / (1.f - alpha);
-            const float w = alpha * T;  // d(pixel channel)/d(colour), also d(pixel depth)/d(depth)
-
-            // colour: accum_rec = colour blended behind this Gaussian (backward.cu:563-576)
-            acc_r = last_alpha * last_r + (1.f - last_alpha) * acc_r;
-            acc_g = last_alpha * last_g + (1.f - last_alpha) * acc_g;
-            acc_b = last_alpha * last_b + (1.f - last_alpha) * acc_b;
-            acc_d = last_alpha * last_depth + (1.f - last_alpha) * acc_d;
-            last_r = c.x; last_g = c.y; last_b = c.z;
-            float dL_dalpha = (c.x - acc_r) * dpr + (c.y - acc_g) * dpg + (c.z - acc_b) * dpb;
-            g[0] = w * dpr; g[1] = w * dpg; g[2] = w * dpb;
-            dL_dalpha *= T;
-            dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot_dpixel;
-
-            // depth: same alpha and transmittance as colour (T_d == T bit for bit)
-            const float czx = b.z, cyz = b.w;
-            const float depth = c.w - (czx * a.z + cyz * a.w) * dx - (czx * a.w + cyz * b.x) * dy;
-            last_depth = depth;
-            last_alpha = alpha;
-            float dL_dalpha_d = dpd * ((depth - acc_d) * T);
-            dL_dalpha_d += (-T_final / (1.f - alpha)) * bg_dot_ddepth;
-
-            // Per pair only 12 MOMENTS are accumulated; the reference's 12 gradient expressions (backward.cu:575-654)
-            // are linear in them with per-Gaussian coefficients and are formed once per (tile, instance) at flush time:
-            //   t = G (dL/dalpha + dL/dalpha_d),  u = opacity * t  (= dL_dG + dL_dG_d times G),  v = alpha T dL/dpix_depth
-            const float t = G * (dL_dalpha + dL_dalpha_d);
-            const float u = b.y * t;
-            const float v = w * dpd;
-            const float udx = u * dx, udy = u * dy;
-            g[3] = v;
-            g[4] = t;
-            g[5] = udx;
-            g[6] = udy;
-            g[7] = udx * dx;
-            g[8] = udx * dy;
-            g[9] = udy * dy;
-            g[10] = v * dx;
-            g[11] = v * dy;
+#pragma unroll
+            for (int k = 0; k < kG; k++) atomicAdd(dst + k, g[k]);
           }
-          {
-            if (__popc(act) <= 2) {
-              // one or two pixels of the sub-tile see this Gaussian (ellipse edge): add them directly
-              if (active) {
+        } else {
+          // Recursive-halving reduction: at each step a lane keeps half of its running sums and hands the other half to
+          // its partner, so the 12 sums over 32 lanes cost 6+3+2+1+1 = 13 shuffles (a butterfly per value: 60).
+          // Sum k ends up in the lane with red_var == k, which issues ONE fp32 RED to moments[gaussian][k]:
+          // 12 consecutive addresses per instance, fire-and-forget — no shared-memory accumulator (whose float add is
+          // a CAS loop on this architecture), no flush, no extra barrier.
+          float h[6], q[3];
 #pragma unroll
-                for (int k = 0; k < kG; k++) atomicAdd(&sAcc[k * kTilePixels + j], g[k]);
-              }
-            } else {
-              // Recursive-halving reduction: at each step a lane keeps half of its running sums and hands the other
-              // half to its partner, so the 12 sums over 32 lanes cost 6+3+2+1+1 = 13 shuffles (a butterfly per
-              // value would cost 60).  Sum k ends up in lane red_lane_of(k) (and its xor-1 neighbour).
-              float h[6], q[3];
-#pragma unroll
-              for (int i = 0; i < 6; i++) {
-                const float send = b16 ? g[i] : g[i + 6], keep = b16 ? g[i + 6] : g[i];
-                h[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-              }
-#pragma unroll
-              for (int i = 0; i < 3; i++) {
-                const float send = b8 ? h[i] : h[i + 3], keep = b8 ? h[i + 3] : h[i];
-                q[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-              }
-              const float r0 = (b4 ? q[2] : q[0]) + __shfl_xor_sync(0xffffffffu, b4 ? q[0] : q[2], 4);
-              const float r1 = (b4 ? 0.f : q[1]) + __shfl_xor_sync(0xffffffffu, b4 ? q[1] : 0.f, 4);
-              float sum = (b2 ? r1 : r0) + __shfl_xor_sync(0xffffffffu, b2 ? r0 : r1, 2);
-              sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-              if (red_valid) atomicAdd(&sAcc[red_var * kTilePixels + j], sum);
-            }
-            if (lane == 0) atomicOr(&sTouched[j >> 5], 1u << (j & 31));
+          for (int i = 0; i < 6; i++) {
+            const float send = b16 ? g[i] : g[i + 6], keep = b16 ? g[i + 6] : g[i];
+            h[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
           }
+#pragma unroll
+          for (int i = 0; i < 3; i++) {
+            const float send = b8 ? h[i] : h[i + 3], keep = b8 ? h[i + 3] : h[i];
+            q[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+          }
+          const float r0 = (b4 ? q[2] : q[0]) + __shfl_xor_sync(0xffffffffu, b4 ? q[0] : q[2], 4);
+          const float r1 = (b4 ? 0.f : q[1]) + __shfl_xor_sync(0xffffffffu, b4 ? q[1] : 0.f, 4);
+          float sum = (b2 ? r1 : r0) + __shfl_xor_sync(0xffffffffu, b2 ? r0 : r1, 2);
+          sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+          if (red_valid) atomicAdd(dst + red_var, sum);
         }
       }
-    }
-    __syncthreads();
-    // flush: form the 12 gradients of each touched instance from its moments and issue one set of global atomics
-    if (tid < n && ((sTouched[tid >> 5] >> (tid & 31)) & 1u)) {
-      const uint32_t gid = sId[tid];
-      const float4 a = sA[tid], b = sB[tid];
-      const float A = a.z, B = a.w, C = b.x, czx = b.z, cyz = b.w;
-      float m[kG];
-#pragma unroll
-      for (int k = 0; k < kG; k++) m[k] = sAcc[k * kTilePixels + tid];
-      const float v0 = m[3], tt = m[4], ux = m[5], uy = m[6], uxx = m[7], uxy = m[8], uyy = m[9], vx = m[10], vy = m[11];
-      atomicAdd(&dL_dcolors[3 * (size_t)gid + 0], m[0]);
-      atomicAdd(&dL_dcolors[3 * (size_t)gid + 1], m[1]);
-      atomicAdd(&dL_dcolors[3 * (size_t)gid + 2], m[2]);
-      float* wk = work + 8 * (size_t)gid;
-      atomicAdd(&wk[5], v0);                                                                   // dL/ddepth
-      atomicAdd(&dL_dmean2D[3 * (size_t)gid + 0], (-A * ux - B * uy - (czx * A + cyz * B) * v0) * ddelx_dx);
-      atomicAdd(&dL_dmean2D[3 * (size_t)gid + 1], (-C * uy - B * ux - (czx * B + cyz * C) * v0) * ddely_dy);
-      atomicAdd(&wk[0], -0.5f * uxx - czx * vx);                                               // dL/dconic_xx
-      atomicAdd(&wk[1], -0.5f * uxy - cyz * vx - czx * vy);                                    // dL/dconic_xy
-      atomicAdd(&wk[2], -0.5f * uyy - cyz * vy);                                               // dL/dconic_yy
-      atomicAdd(&wk[3], -A * vx - B * vy);                                                     // dL/dcov_zx
-      atomicAdd(&wk[4], -B * vx);  // dL/dcov_yz: the reference omits the conic_yy * dy term (backward.cu:616)
-      atomicAdd(&dL_dopacity[gid], tt);
     }
   }
 }
@@ -308,8 +281,9 @@ __device__ __forceinline__ F3 sh_backward(int idx, const BwdArgs& a, uint8_t cla
 
 __global__ void __launch_bounds__(256)
 gaussian_backward_kernel(BwdArgs a, const int32_t* __restrict__ radii, const uint8_t* __restrict__ clamped,
-                         const float* __restrict__ work, const float* __restrict__ dL_dmean2D,
-                         const float* __restrict__ dL_dcolors, float* __restrict__ dL_dmeans3D,
+                         const float* __restrict__ moments, const Splat* __restrict__ splats, int W, int H,
+                         float* __restrict__ dL_dmean2D, float* __restrict__ dL_dcolors,
+                         float* __restrict__ dL_dopacity, float* __restrict__ dL_dmeans3D,
                          float* __restrict__ dL_dcov3D, float* __restrict__ dL_dsh, float* __restrict__ dL_dscales,
                          float* __restrict__ dL_drots) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -327,10 +301,27 @@ gaussian_backward_kernel(BwdArgs a, const int32_t* __restrict__ radii, const uin
     q = reinterpret_cast<const float4*>(a.rots)[idx];
     cov3d_from_scale_rot(scale, a.scale_modifier, q, cov3);
   }
-  const float4 w0 = reinterpret_cast<const float4*>(work)[2 * (size_t)idx];
-  const float4 w1 = reinterpret_cast<const float4*>(work)[2 * (size_t)idx + 1];
-  const float dc_x = w0.x, dc_y = w0.y, dc_z = w0.z;  // dL/dconic xx, xy, yy
-  const float dL_dcovzx = w0.w, dL_dcovyz = w1.x, dL_ddepth = w1.y;
+  // ---- render gradients from the moments (reference expressions: backward.cu:604-654) ----
+  const float4 m0 = reinterpret_cast<const float4*>(moments)[3 * (size_t)idx];
+  const float4 m1 = reinterpret_cast<const float4*>(moments)[3 * (size_t)idx + 1];
+  const float4 m2 = reinterpret_cast<const float4*>(moments)[3 * (size_t)idx + 2];
+  const float v0 = m0.w, tt = m1.x, ux = m1.y, uy = m1.z, uxx = m1.w, uxy = m2.x, uyy = m2.y, vx = m2.z, vy = m2.w;
+  const Splat sp = splats[idx];
+  const float cA = sp.a.z, cB = sp.a.w, cC = sp.b.x, czx = sp.b.z, cyz = sp.b.w;
+  dL_dcolors[3 * (size_t)idx + 0] = m0.x;
+  dL_dcolors[3 * (size_t)idx + 1] = m0.y;
+  dL_dcolors[3 * (size_t)idx + 2] = m0.z;
+  dL_dopacity[idx] = tt;
+  const float g2x = (-cA * ux - cB * uy - (czx * cA + cyz * cB) * v0) * (0.5f * W);
+  const float g2y = (-cC * uy - cB * ux - (czx * cB + cyz * cC) * v0) * (0.5f * H);
+  dL_dmean2D[3 * (size_t)idx + 0] = g2x;
+  dL_dmean2D[3 * (size_t)idx + 1] = g2y;
+  const float dc_x = -0.5f * uxx - czx * vx;             // dL/dconic_xx
+  const float dc_y = -0.5f * uxy - cyz * vx - czx * vy;  // dL/dconic_xy
+  const float dc_z = -0.5f * uyy - cyz * vy;             // dL/dconic_yy
+  const float dL_dcovzx = -cA * vx - cB * vy;
+  const float dL_dcovyz = -cB * vx;  // the reference omits the conic_yy * dy term (backward.cu:616)
+  const float dL_ddepth = v0;
 
   // ---- 2D covariance backward (backward.cu:144-294) ----
   const Ewa e = ewa_project(mean, a.focal_x, a.focal_y, a.tan_fovx, a.tan_fovy, cov3, a.view);
@@ -415,14 +406,13 @@ gaussian_backward_kernel(BwdArgs a, const int32_t* __restrict__ radii, const uin
   dmean.z += dL_ddepth * (vm[10] - vm[11] * mul);
   const float mul1 = (proj[0] * mean.x + proj[4] * mean.y + proj[8] * mean.z + proj[12]) * m_w * m_w;
   const float mul2 = (proj[1] * mean.x + proj[5] * mean.y + proj[9] * mean.z + proj[13]) * m_w * m_w;
-  const float g2x = dL_dmean2D[3 * (size_t)idx + 0], g2y = dL_dmean2D[3 * (size_t)idx + 1];
   dmean.x += (proj[0] * m_w - proj[3] * mul1) * g2x + (proj[1] * m_w - proj[3] * mul2) * g2y;
   dmean.y += (proj[4] * m_w - proj[7] * mul1) * g2x + (proj[5] * m_w - proj[7] * mul2) * g2y;
   dmean.z += (proj[8] * m_w - proj[11] * mul1) * g2x + (proj[9] * m_w - proj[11] * mul2) * g2y;
 
   // ---- SH path ----
   if (a.shs) {
-    const F3 dRGB = {dL_dcolors[3 * (size_t)idx], dL_dcolors[3 * (size_t)idx + 1], dL_dcolors[3 * (size_t)idx + 2]};
+    const F3 dRGB = {m0.x, m0.y, m0.z};
     const F3 dm = sh_backward(idx, a, clamped[idx], dRGB, dL_dsh);
     dmean = dmean + dm;
   }
@@ -481,7 +471,7 @@ extern int g_render_cull;
 
 using namespace gsicp;
 
-extern "C" size_t gsicp_raster_backward_work_bytes(int P) { return (size_t)(P > 0 ? P : 0) * 8 * sizeof(float) + 16; }
+extern "C" size_t gsicp_raster_backward_work_bytes(int P) { return (size_t)(P > 0 ? P : 0) * kG * sizeof(float) + 16; }
 
 extern "C" int gsicp_raster_backward(const gsicp_raster_args* args, int num_rendered, const int32_t* d_radii,
                                      const void* d_geom, const void* d_binning, const void* d_image,
@@ -513,12 +503,12 @@ extern "C" int gsicp_raster_backward(const gsicp_raster_args* args, int num_rend
     ProfScope ps(kProfRenderBwd, stream);
     if (g_render_cull) {
       GSICP_LAUNCH(render_backward_kernel<true>, tiles, kTilePixels, 0, stream, img.tile_order, img.ranges, bin.point_list, W, H, tiles_x,
-                   args->d_background, geom.splats, img.final_T, img.n_contrib, d_dL_dout_color, d_dL_dout_depth,
-                   d_dL_dmeans2D, d_dL_dcolors, d_dL_dopacity, work, shard_count, shard_index);
+                   args->d_background, geom.splats, img.final_T, img.n_contrib, d_dL_dout_color, d_dL_dout_depth, work,
+                   shard_count, shard_index);
     } else {
       GSICP_LAUNCH(render_backward_kernel<false>, tiles, kTilePixels, 0, stream, img.tile_order, img.ranges, bin.point_list, W, H, tiles_x,
-                   args->d_background, geom.splats, img.final_T, img.n_contrib, d_dL_dout_color, d_dL_dout_depth,
-                   d_dL_dmeans2D, d_dL_dcolors, d_dL_dopacity, work, shard_count, shard_index);
+                   args->d_background, geom.splats, img.final_T, img.n_contrib, d_dL_dout_color, d_dL_dout_depth, work,
+                   shard_count, shard_index);
     }
     if (args->debug) GSICP_CUDA(cudaStreamSynchronize(stream));
   }
@@ -533,8 +523,8 @@ extern "C" int gsicp_raster_backward(const gsicp_raster_args* args, int num_rend
   ba.shs = args->d_shs; ba.cov_pre = args->d_cov3D_precomp; ba.view = args->d_viewmatrix; ba.proj = args->d_projmatrix;
   ba.campos = args->d_campos;
   ProfScope ps_gb(kProfGaussBwd, stream);
-  GSICP_LAUNCH(gaussian_backward_kernel, (P + 255) / 256, 256, 0, stream, ba, d_radii, geom.clamped, work, d_dL_dmeans2D,
-               d_dL_dcolors, d_dL_dmeans3D, d_dL_dcov3D, d_dL_dsh, d_dL_dscales, d_dL_drotations);
+  GSICP_LAUNCH(gaussian_backward_kernel, (P + 255) / 256, 256, 0, stream, ba, d_radii, geom.clamped, work, geom.splats, W, H,
+               d_dL_dmeans2D, d_dL_dcolors, d_dL_dopacity, d_dL_dmeans3D, d_dL_dcov3D, d_dL_dsh, d_dL_dscales, d_dL_drotations);
   if (args->debug) GSICP_CUDA(cudaStreamSynchronize(stream));
   GSICP_CUDA(cudaGetLastError());
   return GSICP_OK;

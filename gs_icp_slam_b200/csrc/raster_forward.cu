@@ -248,7 +248,8 @@ render_forward_kernel(const uint32_t* __restrict__ tile_order, const uint2* __re
   const bool inside = px < W && py < H;
   const float pxf = (float)px, pyf = (float)py;
 
-  __shared__ float4 sA[kTilePixels], sB[kTilePixels], sC[kTilePixels];
+  // double-buffered staging of 256 instances: one barrier per batch, loads of batch k+1 overlap the blending of batch k
+  __shared__ float4 sA2[2][kTilePixels], sB2[2][kTilePixels], sC2[2][kTilePixels];
 
   const uint2 range = ranges[tile];
   const int total = (int)(range.y - range.x);
@@ -256,17 +257,26 @@ render_forward_kernel(const uint32_t* __restrict__ tile_order, const uint2* __re
   float T = 1.f, Cr = 0.f, Cg = 0.f, Cb = 0.f, D = 0.f;
   uint32_t last = 0;
 
-  for (int base = 0; base < total; base += kTilePixels) {
-    if (__syncthreads_count(done) == kTilePixels) break;
+  auto stage = [&](int base, int buf) {
     const int n = min(kTilePixels, total - base);
     if (tid < n) {
       const uint32_t g = point_list[range.x + base + tid];
       const Splat* sp = splats + g;
-      sA[tid] = __ldg(&sp->a);
-      sB[tid] = __ldg(&sp->b);
-      sC[tid] = __ldg(&sp->c);
+      sA2[buf][tid] = __ldg(&sp->a);
+      sB2[buf][tid] = __ldg(&sp->b);
+      sC2[buf][tid] = __ldg(&sp->c);
     }
-    __syncthreads();
+  };
+  if (total > 0) stage(0, 0);
+
+  for (int base = 0, buf = 0; base < total; base += kTilePixels, buf ^= 1) {
+    // barrier: batch `base` is staged and every warp is done with the other buffer; also the block-wide early exit
+    if (__syncthreads_count(done) == kTilePixels) break;
+    if (base + kTilePixels < total) stage(base + kTilePixels, buf ^ 1);
+    const int n = min(kTilePixels, total - base);
+    const float4* sA = sA2[buf];
+    const float4* sB = sB2[buf];
+    const float4* sC = sC2[buf];
     if (__all_sync(0xffffffffu, done)) continue;
 
     for (int c0 = 0; c0 < n; c0 += 32) {

@@ -132,7 +132,11 @@ class FastGICP:
             raise TypeError("initial_guess must be 4x4")
         out = np.empty((4, 4), dtype=np.float32)
         self.last_iterations = check(lib.gsicp_gicp_align(self._h, g.ctypes.data, out.ctypes.data), "align")
+        self._final = out.copy()
         return out
+
+    def get_final_transformation(self):  # LsqRegistration binding, main.cpp:171
+        return getattr(self, "_final", np.eye(4, dtype=np.float32)).copy()
 
     def has_converged(self):
         return bool(check(lib.gsicp_gicp_has_converged(self._h)))

@@ -77,6 +77,45 @@ def test_forward_backward_vs_reference_cuda(cuda, P, size, degree, seed):
     ref.free()
 
 
+def test_precomputed_colors_and_cov3d_vs_reference_cuda(cuda):
+    """The alternative inputs of GaussianRasterizer.forward: colors_precomp instead of SHs, cov3D_precomp instead of
+    scale/rotation (DGR/diff_gaussian_rasterization/__init__.py:189-222)."""
+    from gs_icp_slam_b200 import rasterizer as R
+    from oracle import ref_cuda
+
+    if not ref_cuda.available():
+        pytest.skip("oracle/_ref/libref_cuda.so not built")
+    P, (W, H) = 30000, (320, 240)
+    g, cm, t, c, cam = scene_tensors(P, 23, cuda, size=(W, H))
+    gen = torch.Generator(device="cpu").manual_seed(1)
+    colors = torch.rand((P, 3), generator=gen).to(cuda)
+    # Sigma = Rm diag(s^2) Rm^T with Rm the rotation of the (x,y,z,w) quaternion (forward.cu:122-168), upper triangle
+    q, s = t["rotations"].double(), t["scales"].double()
+    x, y, z, w = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
+    Rm = torch.stack([1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y), 2 * (x * y + w * z),
+                      1 - 2 * (x * x + z * z), 2 * (y * z - w * x), 2 * (x * z - w * y), 2 * (y * z + w * x),
+                      1 - 2 * (x * x + y * y)], 1).view(P, 3, 3)
+    Sg = Rm @ torch.diag_embed(s * s) @ Rm.transpose(1, 2)
+    cov = torch.stack([Sg[:, 0, 0], Sg[:, 0, 1], Sg[:, 0, 2], Sg[:, 1, 1], Sg[:, 1, 2], Sg[:, 2, 2]], 1).float().contiguous()
+    bg = torch.tensor([0.2, 0.1, 0.4], device=cuda)
+    n, depth, color, radii, is_used, geom, binning, img = _ours(t, c, H, W, bg, 0, colors=colors, cov=cov)
+    ref = ref_cuda.RefRaster(bg, t["means3D"], None, colors, t["opacities"].reshape(-1), None, None, cov, c["viewmatrix"],
+                             c["projmatrix"], c["campos"], c["tanfovx"], c["tanfovy"], H, W, 0)
+    assert n == ref.num_rendered and torch.equal(radii, ref.radii)
+    assert torch.equal(color, ref.color) and torch.equal(depth, ref.depth)
+    gcol = torch.randn((3, H, W), generator=gen).to(cuda)
+    gdep = torch.randn((1, H, W), generator=gen).to(cuda)
+    e = torch.Tensor([])
+    ours = R.rasterize_gaussians_backward(bg, t["means3D"], radii, colors, e, e, 1.0, cov, c["viewmatrix"], c["projmatrix"],
+                                          c["tanfovx"], c["tanfovy"], gdep, gcol, e, 0, c["campos"], geom, n, binning, img,
+                                          False)
+    rg = ref.backward(gcol, gdep)
+    for name, o in zip(["means2D", "colors", "opacity", "means3D", "cov3D"], ours[:5]):
+        assert rel_err(o.cpu().numpy(), rg[name].cpu().numpy()) <= 2e-4, name
+    assert ours[5].numel() == 0 and float(ours[6].abs().sum()) == 0 and float(ours[7].abs().sum()) == 0
+    ref.free()
+
+
 def test_cull_is_exact(cuda):
     """Sub-tile culling must not change a single bit of the output."""
     from gs_icp_slam_b200 import _lib
