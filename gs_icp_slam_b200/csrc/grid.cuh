@@ -86,22 +86,22 @@ static __global__ void grid_bbox_kernel(int n, const float* __restrict__ xyz, un
   }
 }
 
-// one thread: choose the cell size so that the dense grid has at most max_cells cells
-static __global__ void grid_setup_kernel(const unsigned int* bb, int n, int max_cells, GridMeta* meta) {
+// choose the cell size so that the dense grid has at most max_cells cells
+__device__ __forceinline__ GridMeta grid_choose(const float lo_in[3], const float hi_in[3], int n, int max_cells) {
   float lo[3], hi[3], ext[3];
   for (int d = 0; d < 3; d++) {
-    lo[d] = ord2f(bb[d]);
-    hi[d] = ord2f(bb[3 + d]);
+    lo[d] = lo_in[d];
+    hi[d] = hi_in[d];
     if (!(hi[d] >= lo[d])) { lo[d] = 0.f; hi[d] = 0.f; }
     ext[d] = hi[d] - lo[d];
   }
   const float emax = fmaxf(ext[0], fmaxf(ext[1], ext[2]));
   const double vol = (double)fmaxf(ext[0], emax * 1e-3f) * fmaxf(ext[1], emax * 1e-3f) * fmaxf(ext[2], emax * 1e-3f);
-  // aim at ~2 cells per point (SURVEY §7: surfaces fill few cells; ~5-10 points per occupied cell)
+  // aim at ~2 cells per point (surfaces fill few cells; ~5-10 points per occupied cell)
   const double target = fmin((double)max_cells, fmax(64.0, 2.0 * (double)n));
   float cell = (float)cbrt(vol / target);
   if (!(cell > 0.f)) cell = 1.f;
-  int nx, ny, nz;
+  int nx = 1, ny = 1, nz = 1;
   for (int it = 0; it < 64; it++) {
     nx = (int)fminf(ext[0] / cell, 2.0e6f) + 1;
     ny = (int)fminf(ext[1] / cell, 2.0e6f) + 1;
@@ -109,11 +109,22 @@ static __global__ void grid_setup_kernel(const unsigned int* bb, int n, int max_
     if ((double)nx * ny * nz <= (double)max_cells) break;
     cell *= 1.25f;
   }
-  meta->ox = lo[0]; meta->oy = lo[1]; meta->oz = lo[2];
-  meta->cell = cell;
-  meta->inv_cell = 1.0f / cell;
-  meta->nx = nx; meta->ny = ny; meta->nz = nz;
-  meta->ncells = nx * ny * nz;
+  GridMeta m;
+  m.ox = lo[0]; m.oy = lo[1]; m.oz = lo[2];
+  m.cell = cell;
+  m.inv_cell = 1.0f / cell;
+  m.nx = nx; m.ny = ny; m.nz = nz;
+  m.ncells = nx * ny * nz;
+  return m;
+}
+
+static __global__ void grid_setup_kernel(const unsigned int* bb, int n, int max_cells, GridMeta* meta) {
+  float lo[3], hi[3];
+  for (int d = 0; d < 3; d++) {
+    lo[d] = ord2f(bb[d]);
+    hi[d] = ord2f(bb[3 + d]);
+  }
+  *meta = grid_choose(lo, hi, n, max_cells);
 }
 
 __device__ __forceinline__ int3 grid_cell_of(const GridMeta& m, float x, float y, float z) {
@@ -144,6 +155,108 @@ static __global__ void grid_scatter_kernel(int n, const float* __restrict__ xyz,
   if (i >= n) return;
   const uint32_t slot = atomicAdd(&cursor[cell_of_pt[i]], 1u);
   pts[slot] = make_float4(xyz[3 * (size_t)i], xyz[3 * (size_t)i + 1], xyz[3 * (size_t)i + 2], __uint_as_float((uint32_t)i));
+}
+
+// Whole grid build in ONE CTA for small clouds (the tracker's 12k-point source cloud is rebuilt every frame): bbox,
+// cell size, histogram, exclusive scan and scatter are phases of a single launch separated by block barriers instead of
+// nine dependent launches (whose launch gaps, not their work, dominated: 49 us -> ~12 us on a B200).
+constexpr int kSmallGridThreads = 1024;
+constexpr int kSmallGridMaxPoints = 65536;
+
+static __global__ void __launch_bounds__(kSmallGridThreads)
+grid_build_small_kernel(int n, const float* __restrict__ xyz, int max_cells, GridMeta* __restrict__ meta_out,
+                        uint32_t* __restrict__ cell_start, uint32_t* __restrict__ cursor, uint32_t* __restrict__ cell_of_pt,
+                        float4* __restrict__ pts) {
+  __shared__ float s_lo[3][32], s_hi[3][32];
+  __shared__ GridMeta s_meta;
+  __shared__ uint32_t s_part[kSmallGridThreads / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // phase 1: bounding box
+  float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+  for (int i = tid; i < n; i += kSmallGridThreads) {
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+      const float v = xyz[3 * (size_t)i + d];
+      if (v == v) {
+        mn[d] = fminf(mn[d], v);
+        mx[d] = fmaxf(mx[d], v);
+      }
+    }
+  }
+#pragma unroll
+  for (int d = 0; d < 3; d++) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      mn[d] = fminf(mn[d], __shfl_xor_sync(0xffffffffu, mn[d], o));
+      mx[d] = fmaxf(mx[d], __shfl_xor_sync(0xffffffffu, mx[d], o));
+    }
+    if (lane == 0) {
+      s_lo[d][warp] = mn[d];
+      s_hi[d][warp] = mx[d];
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    float lo[3], hi[3];
+    for (int d = 0; d < 3; d++) {
+      lo[d] = FLT_MAX;
+      hi[d] = -FLT_MAX;
+      for (int w = 0; w < kSmallGridThreads / 32; w++) {
+        lo[d] = fminf(lo[d], s_lo[d][w]);
+        hi[d] = fmaxf(hi[d], s_hi[d][w]);
+      }
+    }
+    s_meta = grid_choose(lo, hi, n, max_cells);
+    *meta_out = s_meta;
+  }
+  __syncthreads();
+  const GridMeta m = s_meta;
+  // phase 2: histogram of points per cell (cell_start doubles as the count array)
+  for (int c = tid; c <= m.ncells; c += kSmallGridThreads) cell_start[c] = 0u;
+  __syncthreads();
+  for (int i = tid; i < n; i += kSmallGridThreads) {
+    const int3 c = grid_cell_of(m, xyz[3 * (size_t)i], xyz[3 * (size_t)i + 1], xyz[3 * (size_t)i + 2]);
+    const uint32_t id = (uint32_t)((c.z * m.ny + c.y) * m.nx + c.x);
+    cell_of_pt[i] = id;
+    atomicAdd(&cell_start[id], 1u);
+  }
+  __syncthreads();
+  // phase 3: exclusive scan over the cells: each thread owns a contiguous chunk
+  const int per = (m.ncells + kSmallGridThreads) / kSmallGridThreads;  // covers indices 0..ncells
+  const int c0 = tid * per, c1 = min(c0 + per, m.ncells + 1);
+  uint32_t local = 0;
+  for (int c = c0; c < c1; c++) local += cell_start[c];
+  uint32_t incl = local;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) s_part[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t v = s_part[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t u = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= o) v += u;
+    }
+    s_part[lane] = v;  // inclusive over warps
+  }
+  __syncthreads();
+  uint32_t run = (incl - local) + (warp > 0 ? s_part[warp - 1] : 0u);
+  for (int c = c0; c < c1; c++) {
+    const uint32_t cnt = cell_start[c];
+    cell_start[c] = run;
+    cursor[c] = run;
+    run += cnt;
+  }
+  __syncthreads();
+  // phase 4: scatter into cell order
+  for (int i = tid; i < n; i += kSmallGridThreads) {
+    const uint32_t slot = atomicAdd(&cursor[cell_of_pt[i]], 1u);
+    pts[slot] = make_float4(xyz[3 * (size_t)i], xyz[3 * (size_t)i + 1], xyz[3 * (size_t)i + 2], __uint_as_float((uint32_t)i));
+  }
 }
 
 // ---- device-side storage ----------------------------------------------------------------------
@@ -179,6 +292,12 @@ struct DeviceGrid {
     cub::DeviceScan::ExclusiveSum(nullptr, tmp, cursor.as<uint32_t>(), cell_start.as<uint32_t>(), max_cells + 1, stream);
     if ((e = cub_tmp.ensure(tmp))) return e;
 
+    if (n <= kSmallGridMaxPoints) {
+      GSICP_LAUNCH(grid_build_small_kernel, 1, kSmallGridThreads, 0, stream, n, d_xyz, max_cells, meta_buf.as<GridMeta>(),
+                   cell_start.as<uint32_t>(), cursor.as<uint32_t>(), cell_of_pt.as<uint32_t>(), pts.as<float4>());
+      GSICP_CUDA(cudaGetLastError());
+      return GSICP_OK;
+    }
     GSICP_LAUNCH(grid_bbox_init_kernel, 1, 32, 0, stream, bbox_buf.as<unsigned int>());
     int blocks = (n + 255) / 256;
     if (blocks > 592) blocks = 592;
