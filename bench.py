@@ -156,6 +156,7 @@ class Ours:
 
             self.dist, self.sharding = dist, sharding
             rasterizer.set_tile_shard(world, rank)
+            rasterizer.set_allreduce(sharding.make_raster_allreduce(dev))  # moments of the visible Gaussians, inside backward
             self.pix_mask = sharding.tile_owner_mask(H, W, world, rank, dev)
             self.reg.set_shard(world, rank, sharding.make_gicp_allreduce(dev))
         self.pose = frames[0]["c2w"].astype(np.float32)
@@ -224,8 +225,6 @@ class Ours:
             loss = sh.sharded_l1(color, gt_rgb, self.pix_mask, gt_rgb.numel()) + 0.1 * sh.sharded_l1(depth, gt_depth, self.pix_mask, gt_depth.numel())
         n_rendered = getattr(color.grad_fn, "num_rendered", 0) if color.grad_fn is not None else 0
         loss.backward()
-        if self.world > 1:
-            self.sharding.allreduce_grads([m[k] for k in ("means3D", "shs", "opacities", "scales", "rotations")])
         lv = float(loss.item())  # D2H read of the step's result
         st["d2h"] += 8
         for k in m:
@@ -482,8 +481,9 @@ def main():
             "gicp_error": 12 * n_src + 60 * n_corr + 8,
             "preprocess": 56 * args.gaussians + 5 * args.gaussians + 79 * V,
             "gaussian_backward": V * 139 + args.gaussians * 64,
-            "tile_sort": 12 * R * 2 * 2,
-            "depth_sort": 8 * args.gaussians * 2 * 4 + 8 * args.gaussians,
+            "tile_sort": 12 * R,
+            "tile_scan": 24 * tiles,
+            "emit_instances": 52 * V + 4 * args.gaussians + 8 * R,
             "gicp_covariance": 160 * n_src + 60 * n_src,
         }
         for name, (ms, n) in prof.items():

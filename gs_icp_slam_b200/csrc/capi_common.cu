@@ -71,7 +71,7 @@ void prof_end(int k, cudaStream_t s) {
 }
 }  // namespace gsicp
 
-static const char* kProfNames[gsicp::kProfCount] = {"preprocess", "depth_sort", "emit_instances", "tile_sort",
+static const char* kProfNames[gsicp::kProfCount] = {"preprocess", "tile_scan", "emit_instances", "tile_sort",
                                                     "render_forward", "render_backward", "gaussian_backward",
                                                     "gicp_covariance", "gicp_linearize", "gicp_error", "grid_build",
                                                     "dist2"};

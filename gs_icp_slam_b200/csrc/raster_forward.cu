@@ -1,16 +1,18 @@
 // raster_forward.cu — forward pass of the B200 Gaussian-splat rasterizer.
 //
 // Replaces CudaRasterizer::Rasterizer::forward (DGR/cuda_rasterizer/rasterizer_impl.cu:201-347):
-//   preprocess -> scan -> duplicateWithKeys -> 64-bit radix sort -> identifyTileRanges -> render
-// with a pipeline re-designed around HBM traffic:
-//   preprocess (writes one 48-B splat record per visible Gaussian + its depth key)
-//   -> 32-bit depth sort of the P Gaussians (stable; ties keep index order)
-//   -> scan of tiles_touched in depth order -> emit (tile key u16/u32, Gaussian id) per instance
-//   -> STABLE radix sort on the tile key only (ceil(log2 tiles) bits, 2 passes instead of 6)
-//   -> tile ranges -> render.
-// Sorting by depth first and by tile second with a stable sort yields exactly the order of the
-// reference's single sort on (tile << 32 | depth bits): instances of a tile ordered by depth,
-// equal depths by Gaussian index — point_list is bit-identical (tests/test_raster_gpu.py).
+//   preprocess -> scan -> duplicateWithKeys -> 64-bit radix sort of all R instances -> identifyTileRanges -> render
+// with a pipeline re-designed around launch count and HBM traffic:
+//   preprocess   writes one 48-B splat record per visible Gaussian and COUNTS the tiles it touches (atomics on T counters)
+//   tile_scan    one CTA: exclusive scan of the T counts -> per-tile ranges, LPT launch order, R published to the host
+//   emit_binned  every instance is dropped into its tile's range (atomic cursor) as a 64-bit key (depth bits << 32 | id)
+//   tile_sort    one CTA per tile sorts its own range in shared memory (bitonic) and writes the ids to point_list
+//   render
+// The reference's single global sort on (tile << 32 | depth bits) with a stable radix sort orders the instances of a
+// tile by depth and equal depths by Gaussian index; sorting each tile's bucket on (depth bits, index) yields exactly the
+// same list, so point_list is bit-identical (tests/test_raster_gpu.py) — without moving the R x 12-byte pairs through
+// 6 radix passes, and with 5 launches instead of 17.  Tiles holding more than kTileSortCap instances fall back to a
+// segmented radix sort (cub::DeviceSegmentedRadixSort) of the same 64-bit keys.
 #include <cub/cub.cuh>
 #include <mutex>
 #include "host_common.h"
@@ -59,19 +61,12 @@ struct PreArgs {
   int prefiltered, shard_count, shard_index;
 };
 
-constexpr uint32_t kInvisibleKey = 0x7FFFFFFFu;  // sorts after every finite positive depth
-
-__global__ void __launch_bounds__(256)
-preprocess_kernel(PreArgs a, int32_t* __restrict__ radii, uint8_t* __restrict__ is_used, Splat* __restrict__ splats,
-                  uint8_t* __restrict__ clamped, uint32_t* __restrict__ depth_key, uint32_t* __restrict__ ident,
-                  uint32_t* __restrict__ tiles_touched) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= a.P) return;
+// Per-Gaussian part of preprocess.  Returns true (and the tile rectangle) when the Gaussian is visible.
+__device__ __forceinline__ bool preprocess_one(const PreArgs& a, int idx, int32_t* __restrict__ radii,
+                                               uint8_t* __restrict__ is_used, Splat* __restrict__ splats,
+                                               uint8_t* __restrict__ clamped, int& x0, int& y0, int& x1, int& y1) {
   radii[idx] = 0;
   is_used[idx] = 0;
-  tiles_touched[idx] = 0;
-  depth_key[idx] = kInvisibleKey;
-  ident[idx] = idx;
 
   const float3 p = make_float3(a.means[3 * idx], a.means[3 * idx + 1], a.means[3 * idx + 2]);
   const float3 pv = xform_point_4x3(p, a.view);
@@ -80,7 +75,7 @@ preprocess_kernel(PreArgs a, int32_t* __restrict__ radii, uint8_t* __restrict__ 
       printf("Point is filtered although prefiltered is set. This shouldn't happen!");
       __trap();
     }
-    return;
+    return false;
   }
   const float4 ph = xform_point_4x4(p, a.proj);
   const float pw = 1.0f / (ph.w + 0.0000001f);
@@ -104,7 +99,7 @@ preprocess_kernel(PreArgs a, int32_t* __restrict__ radii, uint8_t* __restrict__ 
   const float cyz = e.cov.m[1][2];
 
   const float det = (cxx * cyy - cxy * cxy);
-  if (det == 0.0f) return;
+  if (det == 0.0f) return false;
   const float det_inv = 1.f / det;
   const float conx = cyy * det_inv, cony = -cxy * det_inv, conz = cxx * det_inv;
 
@@ -113,9 +108,8 @@ preprocess_kernel(PreArgs a, int32_t* __restrict__ radii, uint8_t* __restrict__ 
   const float lambda2 = mid - sqrtf(fmaxf(0.1f, mid * mid - det));
   const float my_radius = ceilf(3.f * sqrtf(fmaxf(lambda1, lambda2)));
   const float px = ndc_to_pix(pp.x, a.W), py = ndc_to_pix(pp.y, a.H);
-  int x0, y0, x1, y1;
   tile_rect(px, py, (int)my_radius, a.tiles_x, a.tiles_y, x0, y0, x1, y1);
-  if ((x1 - x0) * (y1 - y0) == 0) return;
+  if ((x1 - x0) * (y1 - y0) == 0) return false;
 
   F3 rgb;
   uint8_t cm = 0;
@@ -132,93 +126,176 @@ preprocess_kernel(PreArgs a, int32_t* __restrict__ radii, uint8_t* __restrict__ 
   s.c = make_float4(rgb.x, rgb.y, rgb.z, pv.z);
   splats[idx] = s;
   radii[idx] = (int)my_radius;
-  depth_key[idx] = __float_as_uint(pv.z);
   is_used[idx] = 1;
-
-  // tile instances this rank owns (tile % shard_count == shard_index)
-  uint32_t n = (uint32_t)((y1 - y0) * (x1 - x0));
-  if (a.shard_count > 1) {
-    n = 0;
-    for (int y = y0; y < y1; y++)
-      for (int x = x0; x < x1; x++) n += ((y * a.tiles_x + x) % a.shard_count == a.shard_index);
-  }
-  tiles_touched[idx] = n;
+  return true;
 }
 
-// tiles_touched gathered into depth order, ready for the prefix sum
-__global__ void gather_counts_kernel(int P, const uint32_t* __restrict__ order, const uint32_t* __restrict__ tiles_touched,
-                                     uint32_t* __restrict__ out) {
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s < P) out[s] = tiles_touched[order[s]];
-}
-
-// One thread per depth-sorted Gaussian: write (tile, id) for every owned tile of its rectangle
-// (reference: duplicateWithKeys, rasterizer_impl.cu:70-111, but keyed by tile only).
-template <typename KeyT>
-__global__ void emit_instances_kernel(int P, const uint32_t* __restrict__ order, const uint32_t* __restrict__ offsets,
-                                      const uint32_t* __restrict__ tiles_touched, const Splat* __restrict__ splats,
-                                      const int32_t* __restrict__ radii, int tiles_x, int tiles_y, int shard_count,
-                                      int shard_index, KeyT* __restrict__ keys, uint32_t* __restrict__ vals) {
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= P) return;
-  const uint32_t g = order[s];
-  if (tiles_touched[g] == 0) return;
-  uint32_t off = (s == 0) ? 0u : offsets[s - 1];
-  const float4 a = splats[g].a;
-  int x0, y0, x1, y1;
-  tile_rect(a.x, a.y, radii[g], tiles_x, tiles_y, x0, y0, x1, y1);
-  for (int y = y0; y < y1; y++) {
-    for (int x = x0; x < x1; x++) {
-      const int t = y * tiles_x + x;
+// Visits, warp-cooperatively, every (visible Gaussian, owned tile) pair of the warp's 32 Gaussians: the rectangle of
+// one visible Gaussian at a time is broadcast and its tiles are spread over the lanes, so the per-tile atomics of a
+// Gaussian are issued in ONE parallel round instead of a serial per-thread loop of dependent atomics.
+// f(payload of that Gaussian, tile) is called by the lane that owns the pair; returns the number of owned tiles of the
+// caller's own Gaussian.
+template <typename F>
+__device__ __forceinline__ uint32_t for_each_owned_tile(bool vis, int x0, int y0, int x1, int y1, int tiles_x,
+                                                        int shard_count, int shard_index, unsigned long long payload, F f) {
+  const int lane = threadIdx.x & 31;
+  uint32_t mine = 0;
+  unsigned m = __ballot_sync(0xffffffffu, vis);
+  while (m) {
+    const int src = __ffs(m) - 1;
+    m &= m - 1;
+    const int rx0 = __shfl_sync(0xffffffffu, x0, src), ry0 = __shfl_sync(0xffffffffu, y0, src);
+    const int rx1 = __shfl_sync(0xffffffffu, x1, src), ry1 = __shfl_sync(0xffffffffu, y1, src);
+    const unsigned long long pl = __shfl_sync(0xffffffffu, payload, src);
+    const int w = rx1 - rx0, n = w * (ry1 - ry0);
+    uint32_t owned = 0;
+    for (int k = lane; k < n; k += 32) {
+      const int t = (ry0 + k / w) * tiles_x + rx0 + k % w;
       if (shard_count > 1 && (t % shard_count) != shard_index) continue;
-      keys[off] = (KeyT)t;
-      vals[off] = g;
-      off++;
+      f(pl, t);
+      owned++;
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) owned += __shfl_xor_sync(0xffffffffu, owned, o);
+    if (lane == src) mine = owned;
   }
+  return mine;
 }
 
-template <typename KeyT>
-__global__ void tile_ranges_kernel(int R, const KeyT* __restrict__ keys, uint2* __restrict__ ranges) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= R) return;
-  const uint32_t cur = keys[i];
-  if (i == 0) {
-    ranges[cur].x = 0;
-  } else {
-    const uint32_t prev = keys[i - 1];
-    if (cur != prev) {
-      ranges[prev].y = i;
-      ranges[cur].x = i;
-    }
-  }
-  if (i == R - 1) ranges[cur].y = R;
+__global__ void __launch_bounds__(256)
+preprocess_kernel(PreArgs a, int32_t* __restrict__ radii, uint8_t* __restrict__ is_used, Splat* __restrict__ splats,
+                  uint8_t* __restrict__ clamped, uint32_t* __restrict__ tiles_touched, uint32_t* __restrict__ tile_count) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // blockDim is a multiple of 32: whole warps stay together
+  int x0 = 0, y0 = 0, x1 = 0, y1 = 0;
+  const bool vis = (idx < a.P) && preprocess_one(a, idx, radii, is_used, splats, clamped, x0, y0, x1, y1);
+  // count this Gaussian in every tile it touches that this rank owns (tile % shard_count == shard_index)
+  const uint32_t n = for_each_owned_tile(vis, x0, y0, x1, y1, a.tiles_x, a.shard_count, a.shard_index, 0ull,
+                                         [&](unsigned long long, int t) { atomicAdd(&tile_count[t], 1u); });
+  if (idx < a.P) tiles_touched[idx] = n;
 }
 
-// Launch order of the render CTAs: tiles by decreasing instance count (bucketed by sqrt(count), one CTA).  The
-// hardware dispatches CTAs in index order, so the longest tiles start first and the short ones fill the tail
-// (longest-processing-time-first), instead of a long tile starting last and leaving the other SMs idle.
-__global__ void __launch_bounds__(1024) tile_order_kernel(int tiles, const uint2* __restrict__ ranges, uint32_t* __restrict__ order) {
-  __shared__ uint32_t hist[64], start[64];
-  if (threadIdx.x < 64) hist[threadIdx.x] = 0;
+constexpr int kTileSortCap = 4096;  // instances one CTA sorts in shared memory (32 KB of 64-bit keys)
+
+// One CTA: exclusive scan of the per-tile counts -> ranges and emit cursors, launch order of the render CTAs (tiles by
+// decreasing instance count, bucketed by sqrt(count): the hardware dispatches CTAs in index order, so the longest
+// tiles start first and the short ones fill the tail), and (R, largest tile) published to the host through mapped
+// pinned memory + a sequence word (no memcpy / stream-synchronize calls on the host).
+__global__ void __launch_bounds__(1024)
+tile_scan_kernel(int tiles, const uint32_t* __restrict__ tile_count, uint2* __restrict__ ranges, uint32_t* __restrict__ cursor,
+                 uint32_t* __restrict__ seg_begin, uint32_t* __restrict__ seg_end, uint32_t* __restrict__ order,
+                 volatile unsigned long long* host_map, unsigned long long seq) {
+  __shared__ uint32_t s_warp[32], s_hist[64], s_start[64], s_max[32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid < 64) s_hist[tid] = 0;
+  const int per = (tiles + 1023) / 1024;
+  const int t0 = tid * per, t1 = min(t0 + per, tiles);
+  uint32_t local = 0, lmax = 0;
+  for (int t = t0; t < t1; t++) {
+    const uint32_t c = tile_count[t];
+    local += c;
+    lmax = max(lmax, c);
+  }
+  uint32_t incl = local;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+    lmax = max(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+  }
+  if (lane == 31) s_warp[warp] = incl;
+  if (lane == 0) s_max[warp] = lmax;
   __syncthreads();
-  for (int t = threadIdx.x; t < tiles; t += blockDim.x) {
-    const uint32_t len = ranges[t].y - ranges[t].x;
-    atomicAdd(&hist[min(63, (int)sqrtf((float)len))], 1u);
+  if (warp == 0) {
+    uint32_t v = s_warp[lane], m = s_max[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t u = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= o) v += u;
+      m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    }
+    s_warp[lane] = v;
+    s_max[lane] = m;
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
+  uint32_t run = (incl - local) + (warp > 0 ? s_warp[warp - 1] : 0u);
+  for (int t = t0; t < t1; t++) {
+    const uint32_t c = tile_count[t];
+    ranges[t] = c ? make_uint2(run, run + c) : make_uint2(0u, 0u);  // empty tiles read (0,0) like the reference's zero-filled ranges
+    cursor[t] = run;
+    seg_begin[t] = run;
+    seg_end[t] = run + c;
+    atomicAdd(&s_hist[min(63, (int)sqrtf((float)c))], 1u);
+    run += c;
+  }
+  __syncthreads();
+  if (tid == 0) {
     uint32_t acc = 0;
     for (int b = 63; b >= 0; b--) {
-      start[b] = acc;
-      acc += hist[b];
+      s_start[b] = acc;
+      acc += s_hist[b];
     }
+    host_map[0] = (unsigned long long)s_warp[31];  // R
+    host_map[2] = (unsigned long long)s_max[0];    // largest tile
+    __threadfence_system();
+    host_map[1] = seq;
+    __threadfence_system();
   }
   __syncthreads();
-  for (int t = threadIdx.x; t < tiles; t += blockDim.x) {
-    const uint32_t len = ranges[t].y - ranges[t].x;
-    order[atomicAdd(&start[min(63, (int)sqrtf((float)len))], 1u)] = (uint32_t)t;
+  for (int t = t0; t < t1; t++) order[atomicAdd(&s_start[min(63, (int)sqrtf((float)tile_count[t]))], 1u)] = (uint32_t)t;
+}
+
+// Drop a (depth bits << 32 | id) key into the range of every owned tile of each visible Gaussian's rectangle
+// (reference: duplicateWithKeys, rasterizer_impl.cu:70-111; here the tile is implied by the slot), warp-cooperatively.
+__global__ void __launch_bounds__(256)
+emit_binned_kernel(int P, const uint32_t* __restrict__ tiles_touched, const Splat* __restrict__ splats,
+                   const int32_t* __restrict__ radii, int tiles_x, int tiles_y, int shard_count,
+                   int shard_index, uint32_t* __restrict__ cursor, unsigned long long* __restrict__ keys) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool vis = (g < P) && tiles_touched[g] != 0;
+  int x0 = 0, y0 = 0, x1 = 0, y1 = 0;
+  unsigned long long key = 0;
+  if (vis) {
+    const Splat* sp = splats + g;
+    const float4 a = sp->a;
+    key = ((unsigned long long)__float_as_uint(sp->c.w) << 32) | (unsigned long long)(uint32_t)g;
+    tile_rect(a.x, a.y, radii[g], tiles_x, tiles_y, x0, y0, x1, y1);
   }
+  for_each_owned_tile(vis, x0, y0, x1, y1, tiles_x, shard_count, shard_index, key,
+                      [&](unsigned long long k, int t) { keys[atomicAdd(&cursor[t], 1u)] = k; });
+}
+
+// One CTA per tile: bitonic sort of the tile's keys in shared memory, ids written to point_list.
+__global__ void __launch_bounds__(256)
+tile_sort_kernel(const uint2* __restrict__ ranges, const unsigned long long* __restrict__ keys, uint32_t* __restrict__ point_list) {
+  __shared__ unsigned long long sk[kTileSortCap];
+  const uint2 r = ranges[blockIdx.x];
+  const int n = (int)(r.y - r.x);
+  if (n <= 0 || n > kTileSortCap) return;  // oversized tiles are handled by the segmented-sort fallback
+  int N = 1;
+  while (N < n) N <<= 1;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) sk[i] = (i < n) ? keys[r.x + i] : ~0ull;
+  __syncthreads();
+  for (int k = 2; k <= N; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < (N >> 1); i += blockDim.x) {
+        const int lo = ((i & ~(j - 1)) << 1) | (i & (j - 1));  // insert a 0 bit at position log2(j)
+        const int hi = lo | j;
+        const bool up = ((lo & k) == 0);
+        const unsigned long long x = sk[lo], y = sk[hi];
+        if ((x > y) == up) {
+          sk[lo] = y;
+          sk[hi] = x;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = threadIdx.x; i < n; i += blockDim.x) point_list[r.x + i] = (uint32_t)sk[i];
+}
+
+__global__ void keys_to_ids_kernel(int R, const unsigned long long* __restrict__ keys, uint32_t* __restrict__ point_list) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < R) point_list[i] = (uint32_t)keys[i];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -327,15 +404,6 @@ render_forward_kernel(const uint32_t* __restrict__ tile_order, const uint2* __re
   }
 }
 
-// publishes the instance count into mapped pinned host memory, then bumps the sequence word the host spins on
-__global__ void publish_count_kernel(const uint32_t* __restrict__ last_offset, volatile unsigned long long* host_map,
-                                     unsigned long long seq) {
-  host_map[0] = (unsigned long long)(*last_offset);
-  __threadfence_system();
-  host_map[1] = seq;
-  __threadfence_system();
-}
-
 __global__ void mark_visible_kernel(int P, const float* __restrict__ means, const float* __restrict__ view,
                                     uint8_t* __restrict__ present) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -357,17 +425,11 @@ __global__ void copy_ranges_kernel(int tiles, const uint2* __restrict__ ranges, 
 struct FwdScratch {
   std::mutex mu;
   Scratch per_gaussian, per_instance, cub_tmp;
-  unsigned long long* h_map = nullptr;  // mapped pinned: [0] = num_rendered, [1] = sequence word
+  unsigned long long* h_map = nullptr;  // mapped pinned: [0] = num_rendered, [1] = sequence word, [2] = largest tile
   unsigned long long* d_map = nullptr;
   unsigned long long seq = 0;
 };
 static FwdScratch g_fwd;
-
-static uint32_t bits_for(uint32_t n) {  // smallest b with (1<<b) >= n
-  uint32_t b = 0;
-  while ((1ull << b) < n) b++;
-  return b ? b : 1;
-}
 
 int g_render_cull = 1;  // test hook: 0 renders without sub-tile culling (must give identical output)
 
@@ -414,26 +476,26 @@ extern "C" int gsicp_raster_forward(const gsicp_raster_args* args, float* d_out_
 
   std::lock_guard<std::mutex> lock(g_fwd.mu);
   if (!g_fwd.h_map) {
-    GSICP_CUDA(cudaHostAlloc((void**)&g_fwd.h_map, 2 * sizeof(unsigned long long), cudaHostAllocMapped));
-    g_fwd.h_map[0] = g_fwd.h_map[1] = 0;
+    GSICP_CUDA(cudaHostAlloc((void**)&g_fwd.h_map, 4 * sizeof(unsigned long long), cudaHostAllocMapped));
+    g_fwd.h_map[0] = g_fwd.h_map[1] = g_fwd.h_map[2] = 0;
     GSICP_CUDA(cudaHostGetDevicePointer((void**)&g_fwd.d_map, g_fwd.h_map, 0));
   }
 
   int R = 0;
-  uint32_t *depth_key = nullptr, *ident = nullptr, *depth_sorted = nullptr, *order = nullptr, *tiles_touched = nullptr,
-           *counts = nullptr, *offsets = nullptr;
+  unsigned long long max_tile = 0;
+  uint32_t *tiles_touched = nullptr, *tile_count = nullptr, *cursor = nullptr, *seg_begin = nullptr, *seg_end = nullptr;
   if (P > 0) {
-    // per-Gaussian scratch: 7 x u32[P]
-    const size_t stride = ((size_t)P * 4 + 127) & ~size_t(127);
-    if (int e = g_fwd.per_gaussian.ensure(7 * stride)) return e;
+    // scratch: u32[P] owned-tile counts + 4 x u32[tiles]
+    const size_t pstride = ((size_t)P * 4 + 127) & ~size_t(127);
+    const size_t tstride = ((size_t)tiles * 4 + 127) & ~size_t(127);
+    if (int e = g_fwd.per_gaussian.ensure(pstride + 4 * tstride)) return e;
     char* base = g_fwd.per_gaussian.as<char>();
-    depth_key = (uint32_t*)(base + 0 * stride);
-    ident = (uint32_t*)(base + 1 * stride);
-    depth_sorted = (uint32_t*)(base + 2 * stride);
-    order = (uint32_t*)(base + 3 * stride);
-    tiles_touched = (uint32_t*)(base + 4 * stride);
-    counts = (uint32_t*)(base + 5 * stride);
-    offsets = (uint32_t*)(base + 6 * stride);
+    tiles_touched = (uint32_t*)base;
+    tile_count = (uint32_t*)(base + pstride);
+    cursor = (uint32_t*)(base + pstride + tstride);
+    seg_begin = (uint32_t*)(base + pstride + 2 * tstride);
+    seg_end = (uint32_t*)(base + pstride + 3 * tstride);
+    GSICP_CUDA(cudaMemsetAsync(tile_count, 0, (size_t)tiles * 4, stream));
 
     PreArgs pa;
     pa.P = P; pa.D = args->D; pa.M = args->M; pa.W = W; pa.H = H; pa.tiles_x = tiles_x; pa.tiles_y = tiles_y;
@@ -445,35 +507,22 @@ extern "C" int gsicp_raster_forward(const gsicp_raster_args* args, float* d_out_
     pa.shs = args->d_shs; pa.cov_pre = args->d_cov3D_precomp; pa.col_pre = args->d_colors_precomp;
     pa.view = args->d_viewmatrix; pa.proj = args->d_projmatrix; pa.campos = args->d_campos;
     pa.prefiltered = args->prefiltered; pa.shard_count = shard_count; pa.shard_index = shard_index;
-    const int grid = (P + 255) / 256;
     {
       ProfScope ps(kProfPreprocess, stream);
-      GSICP_LAUNCH(preprocess_kernel, grid, 256, 0, stream, pa, d_radii, d_is_used, geom.splats, geom.clamped, depth_key,
-                   ident, tiles_touched);
+      GSICP_LAUNCH(preprocess_kernel, (P + 255) / 256, 256, 0, stream, pa, d_radii, d_is_used, geom.splats, geom.clamped,
+                   tiles_touched, tile_count);
     }
     if (args->debug) GSICP_CUDA(cudaStreamSynchronize(stream));
 
-    // depth sort (31 significant bits: positive floats and the invisible sentinel)
-    size_t tmp1 = 0, tmp2 = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, tmp1, depth_key, depth_sorted, ident, order, P, 0, 31, stream);
-    cub::DeviceScan::InclusiveSum(nullptr, tmp2, counts, offsets, P, stream);
-    if (int e = g_fwd.cub_tmp.ensure(tmp1 > tmp2 ? tmp1 : tmp2)) return e;
-    size_t tmp = g_fwd.cub_tmp.cap;
-    ProfScope* ps_sort = new ProfScope(kProfDepthSort, stream);
-    GSICP_CUDA(cub::DeviceRadixSort::SortPairs(g_fwd.cub_tmp.ptr, tmp, depth_key, depth_sorted, ident, order, P, 0, 31,
-                                               stream));
-    g_launches.fetch_add(4, std::memory_order_relaxed);
-    GSICP_LAUNCH(gather_counts_kernel, grid, 256, 0, stream, P, order, tiles_touched, counts);
-    tmp = g_fwd.cub_tmp.cap;
-    GSICP_CUDA(cub::DeviceScan::InclusiveSum(g_fwd.cub_tmp.ptr, tmp, counts, offsets, P, stream));
-    delete ps_sort;
-    g_launches.fetch_add(1, std::memory_order_relaxed);
-
-    // The Python API returns num_rendered as a host int (DGR/diff_gaussian_rasterization/__init__.py:96),
-    // and the instance buffers are sized by it: one 4-byte D2H + sync, as in rasterizer_impl.cu:286-287.
-    // The count travels through mapped pinned memory + a sequence word the host spins on (no memcpy / stream-sync calls).
+    // The Python API returns num_rendered as a host int (DGR/diff_gaussian_rasterization/__init__.py:96) and the instance
+    // buffers are sized by it (rasterizer_impl.cu:286-287 does a blocking 4-byte memcpy).  Here the scan kernel publishes
+    // it into mapped pinned memory and the host spins on a sequence word.
     const unsigned long long seq = ++g_fwd.seq;
-    GSICP_LAUNCH(publish_count_kernel, 1, 1, 0, stream, offsets + (P - 1), (volatile unsigned long long*)g_fwd.d_map, seq);
+    {
+      ProfScope ps(kProfDepthSort, stream);  // slot reused: "tile_scan"
+      GSICP_LAUNCH(tile_scan_kernel, 1, 1024, 0, stream, tiles, tile_count, img.ranges, cursor, seg_begin, seg_end,
+                   img.tile_order, (volatile unsigned long long*)g_fwd.d_map, seq);
+    }
     GSICP_CUDA(cudaGetLastError());
     {
       volatile unsigned long long* pm = g_fwd.h_map;
@@ -494,12 +543,15 @@ extern "C" int gsicp_raster_forward(const gsicp_raster_args* args, float* d_out_
           }
         }
       }
+      if (pm[0] > 0x7fffffffull) {
+        set_error("gsicp_raster_forward: instance count overflow");
+        return GSICP_EINVAL;
+      }
       R = (int)pm[0];
+      max_tile = pm[2];
     }
-    if (R < 0) {
-      set_error("gsicp_raster_forward: instance count overflow");
-      return GSICP_EINVAL;
-    }
+  } else {
+    GSICP_CUDA(cudaMemsetAsync(img.ranges, 0, sizeof(uint2) * tiles, stream));
   }
 
   char* bin_p = (char*)binning_alloc(BinState::bytes(R), user);
@@ -509,51 +561,39 @@ extern "C" int gsicp_raster_forward(const gsicp_raster_args* args, float* d_out_
   }
   BinState bin = BinState::from(bin_p, R);
 
-  GSICP_CUDA(cudaMemsetAsync(img.ranges, 0, sizeof(uint2) * tiles, stream));
   if (R > 0) {
-    const bool k16 = tiles <= 65536;
-    const size_t ksz = k16 ? 2 : 4;
-    const size_t kstride = ((size_t)R * ksz + 127) & ~size_t(127);
-    const size_t vstride = ((size_t)R * 4 + 127) & ~size_t(127);
-    if (int e = g_fwd.per_instance.ensure(2 * kstride + vstride)) return e;
-    char* base = g_fwd.per_instance.as<char>();
-    void* keys_in = base;
-    void* keys_out = base + kstride;
-    uint32_t* vals_in = (uint32_t*)(base + 2 * kstride);
-    const int gridP = (P + 255) / 256, gridR = (R + 255) / 256;
-    const int bits = (int)bits_for((uint32_t)tiles);
-    size_t tmp = 0;
-    if (k16) {
-      { ProfScope ps(kProfEmit, stream);
-      GSICP_LAUNCH(emit_instances_kernel<uint16_t>, gridP, 256, 0, stream, P, order, offsets, tiles_touched, geom.splats,
-                   d_radii, tiles_x, tiles_y, shard_count, shard_index, (uint16_t*)keys_in, vals_in); }
-      ProfScope ps_ts(kProfTileSort, stream);
-      cub::DeviceRadixSort::SortPairs(nullptr, tmp, (uint16_t*)keys_in, (uint16_t*)keys_out, vals_in, bin.point_list, R, 0,
-                                      bits, stream);
-      if (int e = g_fwd.cub_tmp.ensure(tmp)) return e;
-      tmp = g_fwd.cub_tmp.cap;
-      GSICP_CUDA(cub::DeviceRadixSort::SortPairs(g_fwd.cub_tmp.ptr, tmp, (uint16_t*)keys_in, (uint16_t*)keys_out, vals_in,
-                                                 bin.point_list, R, 0, bits, stream));
-      GSICP_LAUNCH(tile_ranges_kernel<uint16_t>, gridR, 256, 0, stream, R, (const uint16_t*)keys_out, img.ranges);
-    } else {
-      { ProfScope ps(kProfEmit, stream);
-      GSICP_LAUNCH(emit_instances_kernel<uint32_t>, gridP, 256, 0, stream, P, order, offsets, tiles_touched, geom.splats,
-                   d_radii, tiles_x, tiles_y, shard_count, shard_index, (uint32_t*)keys_in, vals_in); }
-      ProfScope ps_ts(kProfTileSort, stream);
-      cub::DeviceRadixSort::SortPairs(nullptr, tmp, (uint32_t*)keys_in, (uint32_t*)keys_out, vals_in, bin.point_list, R, 0,
-                                      bits, stream);
-      if (int e = g_fwd.cub_tmp.ensure(tmp)) return e;
-      tmp = g_fwd.cub_tmp.cap;
-      GSICP_CUDA(cub::DeviceRadixSort::SortPairs(g_fwd.cub_tmp.ptr, tmp, (uint32_t*)keys_in, (uint32_t*)keys_out, vals_in,
-                                                 bin.point_list, R, 0, bits, stream));
-      GSICP_LAUNCH(tile_ranges_kernel<uint32_t>, gridR, 256, 0, stream, R, (const uint32_t*)keys_out, img.ranges);
+    const size_t kbytes = ((size_t)R * 8 + 127) & ~size_t(127);
+    const bool big = max_tile > (unsigned long long)kTileSortCap;
+    if (int e = g_fwd.per_instance.ensure(big ? 2 * kbytes : kbytes)) return e;
+    unsigned long long* keys = g_fwd.per_instance.as<unsigned long long>();
+    {
+      ProfScope ps(kProfEmit, stream);
+      GSICP_LAUNCH(emit_binned_kernel, (P + 255) / 256, 256, 0, stream, P, tiles_touched, geom.splats, d_radii, tiles_x, tiles_y,
+                   shard_count, shard_index, cursor, keys);
     }
-    g_launches.fetch_add(3, std::memory_order_relaxed);
+    {
+      ProfScope ps(kProfTileSort, stream);
+      if (!big) {
+        GSICP_LAUNCH(tile_sort_kernel, tiles, 256, 0, stream, img.ranges, keys, bin.point_list);
+      } else {
+        // some tile exceeds the shared-memory sort: segmented radix sort of the same 64-bit keys (31 depth bits + id bits)
+        unsigned long long* keys_out = (unsigned long long*)((char*)keys + kbytes);
+        int id_bits = 1;
+        while ((1ull << id_bits) < (unsigned long long)P) id_bits++;
+        size_t tmp = 0;
+        cub::DeviceSegmentedRadixSort::SortKeys(nullptr, tmp, keys, keys_out, R, tiles, seg_begin, seg_end, 0, 64, stream);
+        if (int e = g_fwd.cub_tmp.ensure(tmp)) return e;
+        tmp = g_fwd.cub_tmp.cap;
+        GSICP_CUDA(cub::DeviceSegmentedRadixSort::SortKeys(g_fwd.cub_tmp.ptr, tmp, keys, keys_out, R, tiles, seg_begin, seg_end,
+                                                          0, 64, stream));
+        (void)id_bits;
+        GSICP_LAUNCH(keys_to_ids_kernel, (R + 255) / 256, 256, 0, stream, R, keys_out, bin.point_list);
+      }
+    }
     if (args->debug) GSICP_CUDA(cudaStreamSynchronize(stream));
   }
 
   if (P > 0) {
-    GSICP_LAUNCH(tile_order_kernel, 1, 1024, 0, stream, tiles, img.ranges, img.tile_order);
     ProfScope ps(kProfRenderFwd, stream);
     if (g_render_cull) {
       GSICP_LAUNCH(render_forward_kernel<true>, tiles, kTilePixels, 0, stream, img.tile_order, img.ranges, bin.point_list, W, H, tiles_x,

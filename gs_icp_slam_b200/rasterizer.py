@@ -26,6 +26,30 @@ def set_tile_shard(count, index):
     _tile_shard = (int(count), int(index))
 
 
+_allreduce_cb = None  # keeps the ctypes thunk alive
+
+
+def set_allreduce(fn):
+    """Multi-GPU: fn(device_ptr, count, stream) sums `count` float32 values in place over the ranks (or None to clear).
+    With tile sharding active, rasterize_gaussians_backward then returns the full (already summed) gradients."""
+    global _allreduce_cb
+    if fn is None:
+        _allreduce_cb = _lib.ALLREDUCE_F32_FN()
+    else:
+        def _tramp(_user, ptr, count, stream):
+            try:
+                fn(ptr, count, stream)
+                return 0
+            except Exception as ex:  # never let an exception cross the C boundary
+                import sys
+
+                print(f"rasterizer all-reduce callback failed: {ex}", file=sys.stderr)
+                return 1
+
+        _allreduce_cb = _lib.ALLREDUCE_F32_FN(_tramp)
+    check(lib.gsicp_raster_set_allreduce(_allreduce_cb, None))
+
+
 def _ptr(t):
     """Device pointer of a tensor, or None for the reference's 'not provided' empty tensor."""
     if t is None or t.numel() == 0:

@@ -50,8 +50,8 @@ class DevicePtrArray:
     """Zero-copy view of `count` float64 values at a raw device pointer (CUDA array interface), so the library's
     reduction buffer can be handed to torch.distributed.all_reduce."""
 
-    def __init__(self, ptr, count):
-        self.__cuda_array_interface__ = {"shape": (int(count),), "typestr": "<f8", "data": (int(ptr), False), "version": 3}
+    def __init__(self, ptr, count, typestr="<f8"):
+        self.__cuda_array_interface__ = {"shape": (int(count),), "typestr": typestr, "data": (int(ptr), False), "version": 3}
 
 
 def make_gicp_allreduce(device, group=None):
@@ -60,6 +60,17 @@ def make_gicp_allreduce(device, group=None):
 
     def cb(ptr, count, stream):
         t = torch.as_tensor(DevicePtrArray(ptr, count), device=device)
+        dist.all_reduce(t, group=group)
+
+    return cb
+
+
+def make_raster_allreduce(device, group=None):
+    """Callback for rasterizer.set_allreduce: sums the dense [V][12] fp32 moment buffer over `group` (NCCL)."""
+    import torch.distributed as dist
+
+    def cb(ptr, count, stream):
+        t = torch.as_tensor(DevicePtrArray(ptr, count, "<f4"), device=device)
         dist.all_reduce(t, group=group)
 
     return cb

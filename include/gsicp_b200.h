@@ -101,6 +101,11 @@ int gsicp_raster_forward(const gsicp_raster_args* args,
  * d_work must hold gsicp_raster_backward_work_bytes(P) zero-filled bytes (the reference's
  * dL_dconic[P,6] + dL_ddepths[P] scratch). */
 size_t gsicp_raster_backward_work_bytes(int P);
+/* Multi-GPU (tile-sharded rendering): when set and tile_shard_count > 1, gsicp_raster_backward sums the 12
+ * render moments of the visible Gaussians over the ranks through this callback (in place, fp32, on `stream`) between
+ * the render-backward and the per-Gaussian-backward kernels; every rank then returns the FULL parameter gradients. */
+typedef int (*gsicp_allreduce_f32_fn)(void* user, float* d_buf, size_t count, void* stream);
+int gsicp_raster_set_allreduce(gsicp_allreduce_f32_fn fn, void* user);
 int gsicp_raster_backward(const gsicp_raster_args* args, int num_rendered,
                           const int32_t* d_radii,
                           const void* d_geom, const void* d_binning, const void* d_image,

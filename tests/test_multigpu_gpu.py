@@ -23,6 +23,7 @@ from tests.util import scene_tensors
 
 def render(shard):
     R.set_tile_shard(*( (world, rank) if shard else (1, 0) ))
+    R.set_allreduce(sharding.make_raster_allreduce(dev) if shard else None)
     g, cm, t, c, cam = scene_tensors(20000, 7, dev, size=(320, 240))
     for k in t: t[k].requires_grad_(True)
     m2 = torch.zeros_like(t["means3D"], requires_grad=True)
@@ -32,8 +33,7 @@ def render(shard):
     if shard:
         mask = sharding.tile_owner_mask(240, 320, world, rank, dev)
         loss = sharding.sharded_l1(color, gt, mask, color.numel()) + 0.1 * sharding.sharded_l1(depth, gt[:1], mask, depth.numel())
-        loss.backward()
-        sharding.allreduce_grads([t[k] for k in t])
+        loss.backward()   # the moments of the visible Gaussians are all-reduced inside the rasterizer's backward
         img = color.detach().clone(); dist.all_reduce(img)   # disjoint tiles, zeros elsewhere
     else:
         ((color - gt).abs().mean() + 0.1 * (depth - gt[:1]).abs().mean()).backward()

@@ -61,6 +61,8 @@ if which == "c4":
     gen = torch.Generator(device="cpu").manual_seed(5)
     gcol, gdep = torch.randn((3, H, W), generator=gen).to(dev), torch.randn((1, H, W), generator=gen).to(dev)
     R.set_tile_shard(world, rank)
+    if world > 1:
+        R.set_allreduce(sharding.make_raster_allreduce(dev))
     mask = sharding.tile_owner_mask(H, W, world, rank, dev)
     rs = GaussianRasterizationSettings(H, W, c["tanfovx"], c["tanfovy"], torch.zeros(3, device=dev), 1.0, c["viewmatrix"],
                                        c["projmatrix"], 0, c["campos"], False, False)
@@ -71,8 +73,6 @@ if which == "c4":
                                                            shs=t["shs"], scales=t["scales"], rotations=t["rotations"])
         info["R"] = color.grad_fn.num_rendered
         ((color * gcol * mask).sum() + (depth * gdep * mask).sum()).backward()
-        if world > 1:
-            sharding.allreduce_grads([t[k] for k in t])
         for k in t:
             t[k].grad = None
         m2.grad = None
