@@ -39,6 +39,10 @@ MAP_P = 300000
 MAP_SEED = 3
 
 
+# DRAM bytes per launch from the committed ncu capture of this workload (profiles/r1_ncu_top_kernels.txt)
+NCU_DRAM_BYTES = {"render_backward": 16.73e6, "render_forward": 6.15e6}
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -48,6 +52,10 @@ def parse():
     ap.add_argument("--gaussians", type=int, default=MAP_P)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--multi", default="replicas", choices=["replicas", "shard"],
+                    help="N>1: replicas = one independent SLAM sequence per GPU, no collective (the SLAM loop is sequential in "
+                         "time: SURVEY §8e 'replicas only'); shard = ONE sequence, raster tiles + GICP source points sharded over "
+                         "the ranks with NCCL all-reduces (pays only at C4/C5 sizes, see tools/bench_large.py)")
     ap.add_argument("--overlap", type=int, default=1, help="1: tracker and mapper on two host threads / CUDA streams (default), 0: back to back")
     return ap.parse_args()
 
@@ -118,7 +126,7 @@ class ClockSampler:
 # our implementation
 # ----------------------------------------------------------------------------------------------
 class Ours:
-    def __init__(self, cam, gmap, frames, dev, world, rank):
+    def __init__(self, cam, gmap, frames, dev, world, rank, shard=False):
         import torch
 
         import pygicp
@@ -149,12 +157,15 @@ class Ours:
         self.stage_depth = torch.empty((1, H, W), device=dev)
         self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
         self.pix_mask = None
+        self.count_stats = False
         if world > 1:
             import torch.distributed as dist
 
+            self.dist = dist
+        if world > 1 and shard:
             from gs_icp_slam_b200 import sharding
 
-            self.dist, self.sharding = dist, sharding
+            self.sharding = sharding
             rasterizer.set_tile_shard(world, rank)
             rasterizer.set_allreduce(sharding.make_raster_allreduce(dev))  # moments of the visible Gaussians, inside backward
             self.pix_mask = sharding.tile_owner_mask(H, W, world, rank, dev)
@@ -231,7 +242,8 @@ class Ours:
             m[k].grad = None
         self.means2D.grad = None
         st["R"] += n_rendered
-        st["V"] += int((radii > 0).sum())
+        if self.count_stats:  # bench bookkeeping (a reduction + D2H sync): only in the profiled pass
+            st["V"] += int((radii > 0).sum())
         st["frames"] += 1
         return lv
 
@@ -250,10 +262,19 @@ class Ours:
         self.torch.cuda.set_device(self.dev)
         self.tracker_part(i, resident)
 
-    def enable_overlap(self):
+    def enable_overlap(self, on=True):
         from concurrent.futures import ThreadPoolExecutor
 
+        if not on:
+            if self.pool is not None:
+                self.pool.shutdown(wait=True)
+                self.pool = None
+                self.torch.cuda.synchronize()
+                self.reg.set_stream(self.torch.cuda.current_stream(self.dev).cuda_stream)
+                sys.setswitchinterval(self._switch0)
+            return
         # two Python threads hand the GIL over every switch interval (default 5 ms) when both want it: make it short
+        self._switch0 = sys.getswitchinterval()
         sys.setswitchinterval(2e-5)
         self.pool = ThreadPoolExecutor(max_workers=1)
         self.gicp_stream = self.torch.cuda.Stream(device=self.dev)
@@ -275,6 +296,7 @@ class Ours:
                 torch.cuda.synchronize()
                 self._lib.prof_reset()
                 self._lib.prof_enable(profile)
+                self.count_stats = profile
                 self.launch0 = self._lib.launch_count()
             self.flush.fill_(i & 0xff)  # L2 flush between steps (outside the timed events)
             torch.cuda.synchronize()
@@ -289,7 +311,9 @@ class Ours:
             self.dist.barrier()
         torch.cuda.synchronize()
         self._lib.prof_enable(False)
+        self.count_stats = False
         launches = self._lib.launch_count() - self.launch0
+        self.last_times = times
         return float(np.sum(times)), launches, dict(self.stats)
 
 
@@ -399,8 +423,10 @@ def workload_config(args, **extra):
                      f"max_corr 0.03, keyframe every {KEYFRAME_EVERY} (target refresh), 1 mapper iteration (raster fwd + "
                      "L1 colour/depth loss + raster bwd) per frame",
          "l2": "256 MiB write between steps, excluded from the per-step CUDA-event time",
-         "tracker_mapper": "concurrent (2 host threads, 2 CUDA streams) like the reference's 2 processes" if getattr(args, "overlap", 0) and args.gpus == 1 else "back to back",
-         "parallelism": "single GPU" if args.gpus == 1 else f"tile-sharded rasterizer + point-sharded GICP over {args.gpus} GPUs (NCCL all-reduce)"}
+         "tracker_mapper": getattr(args, "schedule", {"value": "back_to_back", "e2e": "back_to_back"}),
+         "tracker_mapper_note": "back_to_back = one host thread, one stream; concurrent = 2 host threads + 2 CUDA streams like "
+                                "the reference's tracker/mapper processes; both are timed (see schedules), the faster is reported",
+         "parallelism": getattr(args, "parallelism", "single GPU" if args.gpus == 1 else f"{args.gpus} replicas")}
     c.update(extra)
     return c
 
@@ -429,24 +455,31 @@ def main():
 
         dist.init_process_group("nccl", device_id=dev)
     cam, gmap, frames = make_sequence(n_frames, args.gaussians)
-    eng = Ours(cam, gmap, frames, dev, world, rank)
-    if args.overlap and world == 1:
-        eng.enable_overlap()
+    shard = world > 1 and args.multi == "shard"
+    eng = Ours(cam, gmap, frames, dev, world, rank, shard=shard)
     from gs_icp_slam_b200 import _lib
 
     # untimed pre-pass: CUDA module loading, caching-allocator growth and library scratch growth happen here, not in
     # the W warm-up steps of the first timed pass
     eng.run(min(args.steps, 5), 1, resident=False)
     eng.run(min(args.steps, 5), 1, resident=True)
+    # Schedules of the two independent halves of a frame: "back_to_back" (one host thread, one stream) and
+    # "concurrent" (two host threads, two streams, like the reference's tracker/mapper processes).  --overlap 1 times
+    # both, K steps each, and reports the faster one per leg (the concurrent schedule depends on how quickly the host
+    # hands the interpreter lock between the two threads, which varies with the box); both are listed under "schedules".
+    modes = ["back_to_back", "concurrent"] if (args.overlap and not shard) else ["back_to_back"]
+    sched = {}
     with ClockSampler(local_rank) as clk:
-        t_res, launches, st_res = eng.run(args.steps, args.warmup, resident=True)
-        t_e2e, _, st_e2e = eng.run(args.steps, args.warmup, resident=False)
+        for mode in modes:
+            eng.enable_overlap(mode == "concurrent")
+            if mode == "concurrent":
+                eng.run(min(args.steps, 5), 1, resident=True)  # stream / thread start-up, untimed
+            r = eng.run(args.steps, args.warmup, resident=True)
+            tr = list(eng.last_times)
+            e = eng.run(args.steps, args.warmup, resident=False)
+            sched[mode] = {"res": r, "e2e": e, "res_times": tr, "e2e_times": list(eng.last_times)}
     clocks = clk.summary()
-    prof = {}
-    if not args.no_roofline:
-        _, _, st_p = eng.run(args.steps, args.warmup, resident=True, profile=True)
-        prof = _lib.prof_read()
-
+    eng.enable_overlap(False)
     def max_over_ranks(x):
         if world == 1:
             return x
@@ -454,7 +487,19 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    t_res, t_e2e = max_over_ranks(t_res), max_over_ranks(t_e2e)
+    for m in modes:  # device time of a pass = max over the ranks
+        sched[m]["t_res"] = max_over_ranks(sched[m]["res"][0])
+        sched[m]["t_e2e"] = max_over_ranks(sched[m]["e2e"][0])
+    best_res = min(modes, key=lambda m: sched[m]["t_res"])
+    best_e2e = min(modes, key=lambda m: sched[m]["t_e2e"])
+    t_res, t_e2e = sched[best_res]["t_res"], sched[best_e2e]["t_e2e"]
+    _, launches, st_res = sched[best_res]["res"]
+    _, _, st_e2e = sched[best_e2e]["e2e"]
+    args.schedule = {"value": best_res, "e2e": best_e2e}
+    prof, st_p = {}, st_res
+    if not args.no_roofline:
+        _, _, st_p = eng.run(args.steps, args.warmup, resident=True, profile=True)
+        prof = _lib.prof_read()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -495,22 +540,33 @@ def main():
         top = max((k for k in kernels if k in alg), key=lambda k: kernels[k]["ms_per_step"])
         ach = kernels[top]["achieved_GBps"]
         roofline = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                    "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg[top],
+                    "traffic": NCU_DRAM_BYTES.get(top), "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch "
+                    "(profiles/r1_ncu_top_kernels.txt); below the algorithmic bytes because the forward pass leaves the tile lists and "
+                    "splat records in the 126 MB L2", "peak_source": peak_src, "algorithmic_bytes_per_launch": alg[top],
                     "ms_per_launch": kernels[top]["ms_per_launch"],
                     "render_fwd_bwd_GBps": (alg["render_forward"] + alg["render_backward"]) / 1e9 /
                     ((kernels["render_forward"]["ms_per_launch"] + kernels["render_backward"]["ms_per_launch"]) * 1e-3)
                     if "render_forward" in kernels and "render_backward" in kernels else None}
 
-    out = {"metric": "SLAM frames/sec (synthetic 640x480 RGB-D, 300k Gaussians)", "value": K / (t_res * 1e-3),
+    # replicas: every rank walked its own K frames; shard: all ranks worked on the same K frames
+    seqs = 1 if shard else world
+    args.parallelism = ("single GPU" if world == 1 else
+                        f"{world} GPUs, one sequence, raster tiles + GICP source points sharded, NCCL all-reduce" if shard else
+                        f"{world} independent SLAM sequences (replicas), one per GPU, no collective")
+    out = {"metric": "SLAM frames/sec (synthetic 640x480 RGB-D, 300k Gaussians)", "value": seqs * K / (t_res * 1e-3),
            "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": args.warmup, "ms_per_step": t_res / K,
-           "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+           "higher_is_better": True, "scaling": "strong" if shard else "weak", "vs_baseline": None,
            "dtype": "f64 (GICP algebra on f32 points) / f32 (rasterizer)", "data": "synthetic",
            "config": workload_config(args, lm_iterations_per_frame=st_res.get("n_lin", 0) / K,
-                                     tile_instances_per_frame=st_res["R"] / K, visible_gaussians_per_frame=st_res["V"] / K),
+                                     tile_instances_per_frame=st_res["R"] / K, visible_gaussians_per_frame=st_p["V"] / K),
            "clocks": clocks, "gpu_launches": launches,
-           "e2e": {"value": K / (t_e2e * 1e-3), "unit": "frames/s", "ms_per_step": t_e2e / K,
+           "e2e": {"value": seqs * K / (t_e2e * 1e-3), "unit": "frames/s", "ms_per_step": t_e2e / K,
                    "h2d_bytes_per_step": st_e2e["h2d"] / K, "d2h_bytes_per_step": st_e2e["d2h"] / K},
-           "roofline": roofline, "kernels": kernels}
+           "roofline": roofline, "kernels": kernels,
+           "schedules": {m: {"value": seqs * K / (sched[m]["t_res"] * 1e-3), "e2e": seqs * K / (sched[m]["t_e2e"] * 1e-3),
+                             "value_ms_p50_max": [float(np.median(sched[m]["res_times"])), float(np.max(sched[m]["res_times"]))],
+                             "e2e_ms_p50_max": [float(np.median(sched[m]["e2e_times"])), float(np.max(sched[m]["e2e_times"]))]}
+                         for m in modes}}
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(gmap, frames)
     print(json.dumps(out))

@@ -526,6 +526,7 @@ struct Cloud {
   Scratch xyz;         // float [3n]
   Scratch xyz_alt;     // compaction target
   DeviceGrid grid;
+  bool grid_stale = true;  // xyz changed since the grid was built; rebuilt on first use (ensure_grid)
   Scratch cov;         // double [6 * cov_n]
   int cov_n = 0;
   Scratch rots, scales;
@@ -606,6 +607,7 @@ int set_cloud(gsicp_gicp* h, Cloud& c, const void* xyz, int n, int is_f32, bool 
     return GSICP_EINVAL;
   }
   c.n = n;
+  c.grid_stale = true;
   c.clear_cov();
   if (n == 0) return GSICP_OK;
   if (int e = c.xyz.ensure((size_t)n * 3 * sizeof(float))) return e;
@@ -631,8 +633,18 @@ int set_cloud(gsicp_gicp* h, Cloud& c, const void* xyz, int n, int is_f32, bool 
     for (size_t i = 0; i < cnt; i++) out[i] = (float)in[i];
     GSICP_CUDA(cudaMemcpyAsync(c.xyz.ptr, h->h_stage, cnt * sizeof(float), cudaMemcpyHostToDevice, h->stream));
   }
+  c.grid_stale = true;
+  return GSICP_OK;
+}
+
+// The search grid of a cloud is built when a search first needs it: the tracker's source cloud is searched once (its own
+// k-NN), and the compacted cloud a *_with_filter call leaves behind is searched only if it later serves as a target.
+int ensure_grid(gsicp_gicp* h, Cloud& c) {
+  if (!c.grid_stale) return GSICP_OK;
   ProfScope ps(kProfGridBuild, h->stream);
-  return c.grid.build(c.xyz.as<float>(), n, h->stream);
+  if (int e = c.grid.build(c.xyz.as<float>(), c.n, h->stream)) return e;
+  c.grid_stale = false;
+  return GSICP_OK;
 }
 
 int set_filter(gsicp_gicp* h, Cloud& c, int num_trackable, const int32_t* filter, int n) {
@@ -684,6 +696,7 @@ int compute_covariances(gsicp_gicp* h, Cloud& c, bool with_filter, bool clamp) {
   a.filter = d_filter; a.xyz = c.xyz.as<float>(); a.rots = c.rots.as<float>(); a.scales = c.scales.as<float>();
   a.cov = c.cov.as<double>(); a.new_xyz = with_filter ? c.xyz_alt.as<float>() : nullptr;
   const int grid = (n + 127) / 128;
+  if (int e = ensure_grid(h, c)) return e;
   {
   ProfScope ps(kProfCovariance, h->stream);
   const int K = h->k <= 10 ? 10 : (h->k <= 20 ? 20 : 32);
@@ -711,7 +724,7 @@ int compute_covariances(gsicp_gicp* h, Cloud& c, bool with_filter, bool clamp) {
     std::swap(c.xyz, c.xyz_alt);
     c.n = slots;
     c.filter_n = -1;  // consumed; a new cloud needs a new filter
-    if (int e = c.grid.build(c.xyz.as<float>(), c.n, h->stream)) return e;
+    c.grid_stale = true;
   }
   return GSICP_OK;
 }
@@ -831,6 +844,8 @@ int run_linearize(gsicp_gicp* h, const Iso& x, double H[6][6], double b[6], doub
   a.seq = ++h->seq;
   int blocks = (end - begin + kLinBlock - 1) / kLinBlock;
   if (blocks < 1) blocks = 1;
+  if (end > begin)
+    if (int e = ensure_grid(h, h->tgt)) return e;
   { ProfScope ps(kProfLinearize, h->stream);
   if (end > begin) {
     const int nn_blocks = (int)(((size_t)(end - begin) * 32 + 127) / 128);

@@ -259,6 +259,108 @@ grid_build_small_kernel(int n, const float* __restrict__ xyz, int max_cells, Gri
   }
 }
 
+// Same single-CTA build with the cell table in SHARED memory (clouds whose table fits: <= ~25k points, i.e. the
+// tracker's per-frame source cloud): the histogram and the scatter cursor become shared-memory integer atomics and the scan
+// never leaves the SM; global memory sees one read of xyz per phase (L1/L2 hits after the first) and one write of
+// cell_start and pts.
+constexpr int kSmemGridMaxCells = 50 * 1024;  // (cells + 1) * 4 B <= 200 KB of dynamic shared memory
+
+static __global__ void __launch_bounds__(kSmallGridThreads)
+grid_build_smem_kernel(int n, const float* __restrict__ xyz, int max_cells, GridMeta* __restrict__ meta_out,
+                       uint32_t* __restrict__ cell_start, float4* __restrict__ pts) {
+  extern __shared__ uint32_t s_cell[];  // [ncells + 1]: counts -> exclusive starts -> scatter cursors
+  __shared__ float s_lo[3][32], s_hi[3][32];
+  __shared__ GridMeta s_meta;
+  __shared__ uint32_t s_part[kSmallGridThreads / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+  for (int i = tid; i < n; i += kSmallGridThreads) {
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+      const float v = xyz[3 * (size_t)i + d];
+      if (v == v) {
+        mn[d] = fminf(mn[d], v);
+        mx[d] = fmaxf(mx[d], v);
+      }
+    }
+  }
+#pragma unroll
+  for (int d = 0; d < 3; d++) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      mn[d] = fminf(mn[d], __shfl_xor_sync(0xffffffffu, mn[d], o));
+      mx[d] = fmaxf(mx[d], __shfl_xor_sync(0xffffffffu, mx[d], o));
+    }
+    if (lane == 0) {
+      s_lo[d][warp] = mn[d];
+      s_hi[d][warp] = mx[d];
+    }
+  }
+  for (int c = tid; c <= max_cells; c += kSmallGridThreads) s_cell[c] = 0u;
+  __syncthreads();
+  if (warp == 0) {
+    float lo[3], hi[3];
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+      lo[d] = s_lo[d][lane];
+      hi[d] = s_hi[d][lane];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        lo[d] = fminf(lo[d], __shfl_xor_sync(0xffffffffu, lo[d], o));
+        hi[d] = fmaxf(hi[d], __shfl_xor_sync(0xffffffffu, hi[d], o));
+      }
+    }
+    if (lane == 0) {
+      s_meta = grid_choose(lo, hi, n, max_cells);
+      *meta_out = s_meta;
+    }
+  }
+  __syncthreads();
+  const GridMeta m = s_meta;
+  for (int i = tid; i < n; i += kSmallGridThreads) {
+    const int3 c = grid_cell_of(m, xyz[3 * (size_t)i], xyz[3 * (size_t)i + 1], xyz[3 * (size_t)i + 2]);
+    atomicAdd(&s_cell[(c.z * m.ny + c.y) * m.nx + c.x], 1u);
+  }
+  __syncthreads();
+  const int per = (m.ncells + kSmallGridThreads) / kSmallGridThreads;  // covers indices 0..ncells
+  const int c0 = min(tid * per, m.ncells + 1), c1 = min(c0 + per, m.ncells + 1);
+  uint32_t local = 0;
+  for (int c = c0; c < c1; c++) local += s_cell[c];
+  uint32_t incl = local;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) s_part[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t v = s_part[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t u = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= o) v += u;
+    }
+    s_part[lane] = v;
+  }
+  __syncthreads();
+  uint32_t run = (incl - local) + (warp > 0 ? s_part[warp - 1] : 0u);
+  for (int c = c0; c < c1; c++) {
+    const uint32_t cnt = s_cell[c];
+    s_cell[c] = run;
+    run += cnt;
+  }
+  __syncthreads();
+  for (int c = tid; c <= m.ncells; c += kSmallGridThreads) cell_start[c] = s_cell[c];
+  __syncthreads();
+  for (int i = tid; i < n; i += kSmallGridThreads) {
+    const float x = xyz[3 * (size_t)i], y = xyz[3 * (size_t)i + 1], z = xyz[3 * (size_t)i + 2];
+    const int3 c = grid_cell_of(m, x, y, z);
+    const uint32_t slot = atomicAdd(&s_cell[(c.z * m.ny + c.y) * m.nx + c.x], 1u);
+    pts[slot] = make_float4(x, y, z, __uint_as_float((uint32_t)i));
+  }
+}
+
 // ---- device-side storage ----------------------------------------------------------------------
 struct DeviceGrid {
   Scratch meta_buf, bbox_buf, cell_start, cursor, cell_of_pt, pts, cub_tmp;
@@ -292,6 +394,18 @@ struct DeviceGrid {
     cub::DeviceScan::ExclusiveSum(nullptr, tmp, cursor.as<uint32_t>(), cell_start.as<uint32_t>(), max_cells + 1, stream);
     if ((e = cub_tmp.ensure(tmp))) return e;
 
+    if (max_cells <= kSmemGridMaxCells) {
+      static bool attr_set = false;
+      const int smem = (max_cells + 1) * 4;
+      if (!attr_set) {
+        GSICP_CUDA(cudaFuncSetAttribute(grid_build_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (kSmemGridMaxCells + 1) * 4));
+        attr_set = true;
+      }
+      GSICP_LAUNCH(grid_build_smem_kernel, 1, kSmallGridThreads, smem, stream, n, d_xyz, max_cells, meta_buf.as<GridMeta>(),
+                   cell_start.as<uint32_t>(), pts.as<float4>());
+      GSICP_CUDA(cudaGetLastError());
+      return GSICP_OK;
+    }
     if (n <= kSmallGridMaxPoints) {
       GSICP_LAUNCH(grid_build_small_kernel, 1, kSmallGridThreads, 0, stream, n, d_xyz, max_cells, meta_buf.as<GridMeta>(),
                    cell_start.as<uint32_t>(), cursor.as<uint32_t>(), cell_of_pt.as<uint32_t>(), pts.as<float4>());

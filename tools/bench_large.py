@@ -78,7 +78,17 @@ if which == "c4":
         m2.grad = None
 
     ms = timed(it, iters)
+    from gs_icp_slam_b200 import _lib
+
+    _lib.prof_reset()
+    _lib.prof_enable(True)
+    for _ in range(iters):
+        it()
+    torch.cuda.synchronize()
+    _lib.prof_enable(False)
+    kern = {k: round(v[0] / max(v[1], 1) * 1e3, 1) for k, v in _lib.prof_read().items() if v[1]}
     if rank == 0:
+        print(json.dumps({"kernels_us": kern}))
         print(json.dumps({"config": "C4 1280x960, 1M Gaussians, raster fwd+bwd, tile-sharded", "n_gpus": world, "ms_per_iter": ms,
                           "iters_per_s": 1e3 / ms, "tile_instances_this_rank": info["R"]}))
 else:
