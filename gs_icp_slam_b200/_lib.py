@@ -106,6 +106,11 @@ for _n in ("source", "target"):
 _sig("gsicp_gicp_calculate_target_covariance_with_filter", i32, [vp])
 _sig("gsicp_gicp_calculate_source_covariance", i32, [vp])
 _sig("gsicp_gicp_calculate_target_covariance", i32, [vp])
+_sig("gsicp_gicp_calculate_target_covariance_withz", i32, [vp])
+_sig("gsicp_gicp_set_source_z_values", i32, [vp, vp, i32])
+_sig("gsicp_gicp_set_target_z_values", i32, [vp, vp, i32])
+_sig("gsicp_gicp_swap_source_and_target", i32, [vp])
+_sig("gsicp_gicp_get_fitness_score", i32, [vp, C.c_double, vp])
 _sig("gsicp_gicp_align", i32, [vp, vp, vp])
 _sig("gsicp_gicp_has_converged", i32, [vp])
 _sig("gsicp_gicp_get_final_hessian", i32, [vp, vp])

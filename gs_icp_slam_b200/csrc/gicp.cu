@@ -48,6 +48,7 @@ struct CovArgs {
   float* scales;     // [3n]
   double* cov;       // [6 * slots]
   float* new_xyz;    // [3 * num_trackable] (only with filter)
+  const float* z;    // NULL, or per-point z values: exported scales are divided by max(1, z^1.5 * 2) (fgi:534-538)
 };
 
 // k-NN of every point of the cloud in itself, one warp per point: ids and squared distances sorted by (d2, id).
@@ -124,6 +125,12 @@ covariance_kernel(CovArgs a, const uint32_t* __restrict__ nn_id, const float* __
   a.scales[3 * (size_t)i + 0] = (float)sqrt(S[0]);
   a.scales[3 * (size_t)i + 1] = (float)sqrt(S[1]);
   a.scales[3 * (size_t)i + 2] = (float)sqrt(S[2]);
+  if (a.z) {  // calculate_covariances_withz
+    const float z = (float)fmax(1.0, pow((double)a.z[i], 1.5) * 2.0);
+    a.scales[3 * (size_t)i + 0] = __fdiv_rn((float)sqrt(S[0]), z);
+    a.scales[3 * (size_t)i + 1] = __fdiv_rn((float)sqrt(S[1]), z);
+    a.scales[3 * (size_t)i + 2] = __fdiv_rn((float)sqrt(S[2]), z);
+  }
 
   int slot = i;
   if (a.filter) {
@@ -283,6 +290,38 @@ correspond_kernel(GridView tgt, PoseD T, int begin, int end, double max_corr_sq,
   if ((threadIdx.x & 31) == 0) {
     sqd[i] = d2;
     corr[i] = ((tgt.n > 0) && ((double)d2 < max_corr_sq)) ? (int32_t)id : -1;
+  }
+}
+
+// pcl::Registration::getFitnessScore: sum and count of the squared NN distances <= max_range (one CTA, deterministic).
+__global__ void __launch_bounds__(1024)
+fitness_kernel(int n, const float* __restrict__ sqd, double max_range, double* __restrict__ out) {
+  __shared__ double s_sum[32], s_cnt[32];
+  double sum = 0.0, cnt = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const double d = (double)sqd[i];
+    if (d <= max_range) {
+      sum += d;
+      cnt += 1.0;
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    sum += __shfl_down_sync(0xffffffffu, sum, o);
+    cnt += __shfl_down_sync(0xffffffffu, cnt, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    s_sum[threadIdx.x >> 5] = sum;
+    s_cnt[threadIdx.x >> 5] = cnt;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0, c = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); w++) {
+      a += s_sum[w];
+      c += s_cnt[w];
+    }
+    out[0] = a;
+    out[1] = c;
   }
 }
 
@@ -533,6 +572,8 @@ struct Cloud {
   int rots_n = 0, scales_n = 0;  // element counts (4 * N_all, 3 * N_all)
   Scratch filter;      // int32 [filter_n]
   int filter_n = -1, num_trackable = 0;
+  Scratch zvals;       // float [z_n]  (set_*_z_values)
+  int z_n = -1;
   void clear_cov() { cov_n = 0; rots_n = 0; scales_n = 0; }
 };
 
@@ -662,11 +703,15 @@ int set_filter(gsicp_gicp* h, Cloud& c, int num_trackable, const int32_t* filter
 }
 
 // covariances of a cloud; with_filter: keep only trackable points afterwards (fgi:588-706 / 710-825)
-int compute_covariances(gsicp_gicp* h, Cloud& c, bool with_filter, bool clamp) {
+int compute_covariances(gsicp_gicp* h, Cloud& c, bool with_filter, bool clamp, bool withz = false) {
   const int n = c.n;
   if (n == 0) {
     fprintf(stderr, "no point cloud\n");
     return GSICP_OK;
+  }
+  if (withz && c.z_n != n) {  // the reference indexes z_values[i] unchecked (fgi:534)
+    set_error("z values (%d) do not match the cloud size %d", c.z_n, n);
+    return GSICP_ESTATE;
   }
   if (h->k > 32 || h->k < 1) {
     set_error("correspondence randomness k=%d unsupported (1..32)", h->k);
@@ -695,6 +740,7 @@ int compute_covariances(gsicp_gicp* h, Cloud& c, bool with_filter, bool clamp) {
   a.n = n; a.k = h->k; a.knn_max = h->knn_max; a.clamp = clamp ? 1 : 0;
   a.filter = d_filter; a.xyz = c.xyz.as<float>(); a.rots = c.rots.as<float>(); a.scales = c.scales.as<float>();
   a.cov = c.cov.as<double>(); a.new_xyz = with_filter ? c.xyz_alt.as<float>() : nullptr;
+  a.z = withz ? c.zvals.as<float>() : nullptr;
   const int grid = (n + 127) / 128;
   if (int e = ensure_grid(h, c)) return e;
   {
@@ -1062,6 +1108,29 @@ int gsicp_gicp_set_target_filter(gsicp_gicp* h, int nt, const int32_t* f, int n)
 int gsicp_gicp_calculate_target_covariance_with_filter(gsicp_gicp* h) { H_CHECK(h); return compute_covariances(h, h->tgt, true, false); }
 int gsicp_gicp_calculate_source_covariance(gsicp_gicp* h) { H_CHECK(h); return compute_covariances(h, h->src, false, true); }
 int gsicp_gicp_calculate_target_covariance(gsicp_gicp* h) { H_CHECK(h); return compute_covariances(h, h->tgt, false, true); }
+int gsicp_gicp_calculate_target_covariance_withz(gsicp_gicp* h) { H_CHECK(h); return compute_covariances(h, h->tgt, false, true, true); }
+
+static int set_z_values(gsicp_gicp* h, Cloud& c, const float* z, int n) {
+  if (n < 0 || (n > 0 && !z)) return GSICP_EINVAL;
+  if (int e = c.zvals.ensure((size_t)(n > 0 ? n : 1) * sizeof(float))) return e;
+  if (n > 0) GSICP_CUDA(cudaMemcpyAsync(c.zvals.ptr, z, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  c.z_n = n;
+  return GSICP_OK;
+}
+int gsicp_gicp_set_source_z_values(gsicp_gicp* h, const float* z, int n) { H_CHECK(h); return set_z_values(h, h->src, z, n); }
+int gsicp_gicp_set_target_z_values(gsicp_gicp* h, const float* z, int n) { H_CHECK(h); return set_z_values(h, h->tgt, z, n); }
+
+int gsicp_gicp_swap_source_and_target(gsicp_gicp* h) {
+  H_CHECK(h);
+  std::swap(h->src, h->tgt);  // clouds, grids, covariances, rotations, scales (fgi:66-76)
+  std::swap(h->src.filter, h->tgt.filter);  // filters and z values are not swapped by the reference
+  std::swap(h->src.filter_n, h->tgt.filter_n);
+  std::swap(h->src.num_trackable, h->tgt.num_trackable);
+  std::swap(h->src.zvals, h->tgt.zvals);
+  std::swap(h->src.z_n, h->tgt.z_n);
+  h->corr_n = -1;
+  return GSICP_OK;
+}
 
 int gsicp_gicp_set_source_covariances_fromqs(gsicp_gicp* h, const float* r, const float* s, int n) { H_CHECK(h); return covs_from_qs(h, h->src, r, s, n); }
 int gsicp_gicp_set_target_covariances_fromqs(gsicp_gicp* h, const float* r, const float* s, int n) { H_CHECK(h); return covs_from_qs(h, h->tgt, r, s, n); }
@@ -1151,6 +1220,32 @@ int gsicp_gicp_get_source_correspondence(gsicp_gicp* h, int32_t* corr, float* sq
   GSICP_CUDA(cudaMemcpyAsync(corr, h->corr.ptr, (size_t)h->src.n * 4, cudaMemcpyDeviceToHost, h->stream));
   GSICP_CUDA(cudaMemcpyAsync(sq_dist, h->sqd.ptr, (size_t)h->src.n * 4, cudaMemcpyDeviceToHost, h->stream));
   GSICP_CUDA(cudaStreamSynchronize(h->stream));
+  return GSICP_OK;
+}
+
+int gsicp_gicp_get_fitness_score(gsicp_gicp* h, double max_range, double* out) {
+  H_CHECK(h);
+  if (!out) return GSICP_EINVAL;
+  *out = std::numeric_limits<double>::max();
+  const int n = h->src.n;
+  if (n == 0 || h->tgt.n == 0) return GSICP_OK;
+  if (int e = ensure_grid(h, h->tgt)) return e;
+  if (int e = h->nn_id.ensure((size_t)n * 4)) return e;
+  if (int e = h->nn_d2.ensure((size_t)n * 4)) return e;
+  if (int e = h->red_out.ensure(kRed * sizeof(double))) return e;
+  Iso x;
+  for (int i = 0; i < 3; i++) {
+    for (int j = 0; j < 3; j++) x.R[i][j] = (double)h->final_transformation[4 * i + j];
+    x.t[i] = (double)h->final_transformation[4 * i + 3];
+  }
+  const int nn_blocks = (int)(((size_t)n * 32 + 127) / 128);
+  GSICP_LAUNCH(correspond_kernel, nn_blocks, 128, 0, h->stream, h->tgt.grid.view(), make_pose(x), 0, n,
+               std::numeric_limits<double>::infinity(), h->src.xyz.as<float>(), h->nn_id.as<int32_t>(), h->nn_d2.as<float>());
+  GSICP_LAUNCH(fitness_kernel, 1, 1024, 0, h->stream, n, h->nn_d2.as<float>(), max_range, h->red_out.as<double>());
+  double r[2] = {0, 0};
+  GSICP_CUDA(cudaMemcpyAsync(r, h->red_out.ptr, sizeof(r), cudaMemcpyDeviceToHost, h->stream));
+  GSICP_CUDA(cudaStreamSynchronize(h->stream));
+  if (r[1] > 0.0) *out = r[0] / r[1];
   return GSICP_OK;
 }
 

@@ -174,7 +174,12 @@ preprocess_kernel(PreArgs a, int32_t* __restrict__ radii, uint8_t* __restrict__ 
   if (idx < a.P) tiles_touched[idx] = n;
 }
 
-constexpr int kTileSortCap = 4096;  // instances one CTA sorts in shared memory (32 KB of 64-bit keys)
+// Shared-memory tile sort, two size classes (tiles are already ordered by decreasing count in `order`):
+//   small: < 1024 instances — 256 threads, 8 KB of keys (most tiles; many CTAs per SM)
+//   big:   1024 .. kTileSortCap instances — 1024 threads, up to 128 KB of keys
+constexpr int kBigTileBin = 32;                          // sqrt-count bucket where the big class starts
+constexpr int kSmallTileCap = kBigTileBin * kBigTileBin;  // 1024
+constexpr int kTileSortCap = 16384;                      // instances one CTA sorts in shared memory (128 KB of 64-bit keys)
 
 // One CTA: exclusive scan of the per-tile counts -> ranges and emit cursors, launch order of the render CTAs (tiles by
 // decreasing instance count, bucketed by sqrt(count): the hardware dispatches CTAs in index order, so the longest
@@ -234,8 +239,11 @@ tile_scan_kernel(int tiles, const uint32_t* __restrict__ tile_count, uint2* __re
       s_start[b] = acc;
       acc += s_hist[b];
     }
+    uint32_t n_big = 0;
+    for (int b = kBigTileBin; b < 64; b++) n_big += s_hist[b];
     host_map[0] = (unsigned long long)s_warp[31];  // R
     host_map[2] = (unsigned long long)s_max[0];    // largest tile
+    host_map[3] = (unsigned long long)n_big;       // tiles with >= kBigTileBin^2 instances (they lead `order`)
     __threadfence_system();
     host_map[1] = seq;
     __threadfence_system();
@@ -264,20 +272,27 @@ emit_binned_kernel(int P, const uint32_t* __restrict__ tiles_touched, const Spla
                       [&](unsigned long long k, int t) { keys[atomicAdd(&cursor[t], 1u)] = k; });
 }
 
-// One CTA per tile: bitonic sort of the tile's keys in shared memory, ids written to point_list.
-__global__ void __launch_bounds__(256)
-tile_sort_kernel(const uint2* __restrict__ ranges, const unsigned long long* __restrict__ keys, uint32_t* __restrict__ point_list) {
-  __shared__ unsigned long long sk[kTileSortCap];
-  const uint2 r = ranges[blockIdx.x];
+// One CTA per tile: bitonic sort of the tile's keys in shared memory, ids written to point_list.  CTA b sorts tile
+// order[first + b] (the size classes are ranges of `order`); a tile above cap is left to the segmented-sort fallback.
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS)
+tile_sort_kernel(const uint32_t* __restrict__ order, int first, int cap, const uint2* __restrict__ ranges,
+                 const unsigned long long* __restrict__ keys, uint32_t* __restrict__ point_list) {
+  extern __shared__ unsigned long long sk[];
+  const uint2 r = ranges[order[first + blockIdx.x]];
   const int n = (int)(r.y - r.x);
-  if (n <= 0 || n > kTileSortCap) return;  // oversized tiles are handled by the segmented-sort fallback
-  int N = 1;
+  if (n <= 0 || n > cap) return;
+  if (n == 1) {
+    if (threadIdx.x == 0) point_list[r.x] = (uint32_t)keys[r.x];
+    return;
+  }
+  int N = 2;
   while (N < n) N <<= 1;
-  for (int i = threadIdx.x; i < N; i += blockDim.x) sk[i] = (i < n) ? keys[r.x + i] : ~0ull;
+  for (int i = threadIdx.x; i < N; i += THREADS) sk[i] = (i < n) ? keys[r.x + i] : ~0ull;
   __syncthreads();
   for (int k = 2; k <= N; k <<= 1) {
     for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int i = threadIdx.x; i < (N >> 1); i += blockDim.x) {
+      for (int i = threadIdx.x; i < (N >> 1); i += THREADS) {
         const int lo = ((i & ~(j - 1)) << 1) | (i & (j - 1));  // insert a 0 bit at position log2(j)
         const int hi = lo | j;
         const bool up = ((lo & k) == 0);
@@ -290,7 +305,7 @@ tile_sort_kernel(const uint2* __restrict__ ranges, const unsigned long long* __r
       __syncthreads();
     }
   }
-  for (int i = threadIdx.x; i < n; i += blockDim.x) point_list[r.x + i] = (uint32_t)sk[i];
+  for (int i = threadIdx.x; i < n; i += THREADS) point_list[r.x + i] = (uint32_t)sk[i];
 }
 
 __global__ void keys_to_ids_kernel(int R, const unsigned long long* __restrict__ keys, uint32_t* __restrict__ point_list) {
@@ -483,6 +498,7 @@ extern "C" int gsicp_raster_forward(const gsicp_raster_args* args, float* d_out_
 
   int R = 0;
   unsigned long long max_tile = 0;
+  int n_big = 0;
   uint32_t *tiles_touched = nullptr, *tile_count = nullptr, *cursor = nullptr, *seg_begin = nullptr, *seg_end = nullptr;
   if (P > 0) {
     // scratch: u32[P] owned-tile counts + 4 x u32[tiles]
@@ -549,6 +565,7 @@ extern "C" int gsicp_raster_forward(const gsicp_raster_args* args, float* d_out_
       }
       R = (int)pm[0];
       max_tile = pm[2];
+      n_big = (int)pm[3];
     }
   } else {
     GSICP_CUDA(cudaMemsetAsync(img.ranges, 0, sizeof(uint2) * tiles, stream));
@@ -574,7 +591,20 @@ extern "C" int gsicp_raster_forward(const gsicp_raster_args* args, float* d_out_
     {
       ProfScope ps(kProfTileSort, stream);
       if (!big) {
-        GSICP_LAUNCH(tile_sort_kernel, tiles, 256, 0, stream, img.ranges, keys, bin.point_list);
+        if (n_big > 0) {
+          static bool attr_set = false;
+          if (!attr_set) {
+            GSICP_CUDA(cudaFuncSetAttribute(tile_sort_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSortCap * 8));
+            attr_set = true;
+          }
+          int cap = kSmallTileCap;
+          while ((unsigned long long)cap < max_tile) cap <<= 1;
+          GSICP_LAUNCH(tile_sort_kernel<1024>, n_big, 1024, (size_t)cap * 8, stream, img.tile_order, 0, cap, img.ranges,
+                       keys, bin.point_list);
+        }
+        if (tiles > n_big)
+          GSICP_LAUNCH(tile_sort_kernel<256>, tiles - n_big, 256, (size_t)kSmallTileCap * 8, stream, img.tile_order, n_big,
+                       kSmallTileCap, img.ranges, keys, bin.point_list);
       } else {
         // some tile exceeds the shared-memory sort: segmented radix sort of the same 64-bit keys (31 depth bits + id bits)
         unsigned long long* keys_out = (unsigned long long*)((char*)keys + kbytes);

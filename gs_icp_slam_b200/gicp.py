@@ -103,6 +103,20 @@ class FastGICP:
     def calculate_target_covariance_with_filter(self):
         check(lib.gsicp_gicp_calculate_target_covariance_with_filter(self._h))
 
+    def calculate_target_covariance_withz(self):  # main.cpp:228
+        check(lib.gsicp_gicp_calculate_target_covariance_withz(self._h))
+
+    def set_source_z_values(self, z_values):  # main.cpp:246-249
+        z = _f32_1d(z_values)
+        check(lib.gsicp_gicp_set_source_z_values(self._h, z.ctypes.data, len(z)))
+
+    def set_target_z_values(self, z_values):  # main.cpp:250-253
+        z = _f32_1d(z_values)
+        check(lib.gsicp_gicp_set_target_z_values(self._h, z.ctypes.data, len(z)))
+
+    def swap_source_and_target(self):  # main.cpp:169
+        check(lib.gsicp_gicp_swap_source_and_target(self._h))
+
     def _fromqs(self, fn, rotationsq, scales):
         if hasattr(rotationsq, "is_cuda") and rotationsq.is_cuda:  # zero-copy path for CUDA tensors
             r = rotationsq.detach().float().contiguous().view(-1)
@@ -140,6 +154,11 @@ class FastGICP:
 
     def has_converged(self):
         return bool(check(lib.gsicp_gicp_has_converged(self._h)))
+
+    def get_fitness_score(self, max_range):  # main.cpp:172
+        out = C.c_double(0.0)
+        check(lib.gsicp_gicp_get_fitness_score(self._h, float(max_range), C.byref(out)))
+        return out.value
 
     def get_final_hessian(self):
         H = np.empty((6, 6), dtype=np.float64)

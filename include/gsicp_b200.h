@@ -169,6 +169,14 @@ int gsicp_gicp_set_target_filter(gsicp_gicp*, int num_trackable, const int32_t* 
 int gsicp_gicp_calculate_target_covariance_with_filter(gsicp_gicp*);
 int gsicp_gicp_calculate_source_covariance(gsicp_gicp*);
 int gsicp_gicp_calculate_target_covariance(gsicp_gicp*);
+/* main.cpp:228 / fgi:145-154,481-583: as calculate_target_covariance, exported scales divided by max(1, z^1.5 * 2);
+ * GSICP_ESTATE unless set_target_z_values supplied one z per target point. */
+int gsicp_gicp_calculate_target_covariance_withz(gsicp_gicp*);
+int gsicp_gicp_set_source_z_values(gsicp_gicp*, const float* z, int n);     /* main.cpp:246-249, fgi:182-186 */
+int gsicp_gicp_set_target_z_values(gsicp_gicp*, const float* z, int n);     /* main.cpp:250-253, fgi:205-209 */
+/* main.cpp:169 / fgi:66-76: exchanges clouds, search structures, covariances, rotations and scales (filters and z values
+ * stay where they are, as in the reference) and drops the correspondences. */
+int gsicp_gicp_swap_source_and_target(gsicp_gicp*);
 
 /* set_source/target_covariances_fromqs (main.cpp:234-245, fgi:828-902). n = number of points. */
 int gsicp_gicp_set_source_covariances_fromqs(gsicp_gicp*, const float* rots_xyzw, const float* scales, int n);
@@ -182,6 +190,9 @@ int gsicp_gicp_set_target_covariances_fromqs_device(gsicp_gicp*, const float* d_
 int gsicp_gicp_align(gsicp_gicp*, const float guess[16], float out[16]);
 int gsicp_gicp_has_converged(gsicp_gicp*);
 int gsicp_gicp_get_final_hessian(gsicp_gicp*, double out[36]);          /* lsq:44-46 */
+/* main.cpp:172 -> pcl::Registration::getFitnessScore(max_range): mean squared NN distance of the source points, moved by
+ * the final transformation, over those with squared distance <= max_range; DBL_MAX if there is none. */
+int gsicp_gicp_get_fitness_score(gsicp_gicp*, double max_range, double* out);
 
 /* Getters (main.cpp:206-233, fast_gicp.hpp:82-110). *_size return element counts. */
 int gsicp_gicp_source_size(gsicp_gicp*);          /* input_->size() (after filtering: trackable) */

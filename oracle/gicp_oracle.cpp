@@ -412,6 +412,7 @@ struct Cloud {
   std::vector<int> filter;
   bool has_filter = false;
   int num_trackable = 0;
+  std::vector<float> z_values;  // fgi:182-186 / 205-209
 };
 
 constexpr int kChunk = 128;  // reduction granularity of linearize (= the CUDA block size)
@@ -441,9 +442,12 @@ struct Oracle {
     c.scales.clear();
   }
 
-  int covariances(Cloud& c, bool with_filter, bool clamp) {
+  // withz: calculate_covariances_withz (fgi:481-583) = the clamped variant with the exported scales divided by
+  // z = max(1, z_value^1.5 * 2)
+  int covariances(Cloud& c, bool with_filter, bool clamp, bool withz = false) {
     const int n = c.n;
     if (n == 0) { fprintf(stderr, "no point cloud\n"); return 0; }
+    if (withz && (int)c.z_values.size() != n) return -4;
     int slots = n;
     if (with_filter) {
       if (!c.has_filter) {
@@ -487,6 +491,10 @@ struct Oracle {
         quat_from_matrix(U, q);
         for (int d = 0; d < 4; d++) c.rots[4 * (size_t)i + d] = (float)q[d];
         for (int d = 0; d < 3; d++) c.scales[3 * (size_t)i + d] = (float)std::sqrt(S[d]);
+        if (withz) {
+          const float z = (float)std::max(1., std::pow((double)c.z_values[i], 1.5) * 2.);  // fgi:534
+          for (int d = 0; d < 3; d++) c.scales[3 * (size_t)i + d] = (float)std::sqrt(S[d]) / z;
+        }
         int slot = i;
         if (with_filter) {
           if (c.filter[i] == 0) continue;
@@ -774,6 +782,40 @@ void go_set_target_filter(void* h, int nt, const int32_t* f, int n) { set_filter
 int go_calculate_target_covariance_with_filter(void* h) { Oracle* o = (Oracle*)h; return o->covariances(o->tgt, true, false); }
 int go_calculate_source_covariance(void* h) { Oracle* o = (Oracle*)h; return o->covariances(o->src, false, true); }
 int go_calculate_target_covariance(void* h) { Oracle* o = (Oracle*)h; return o->covariances(o->tgt, false, true); }
+int go_calculate_target_covariance_withz(void* h) { Oracle* o = (Oracle*)h; return o->covariances(o->tgt, false, true, true); }
+void go_set_source_z_values(void* h, const float* z, int n) { ((Oracle*)h)->src.z_values.assign(z, z + n); }
+void go_set_target_z_values(void* h, const float* z, int n) { ((Oracle*)h)->tgt.z_values.assign(z, z + n); }
+// swapSourceAndTarget (fgi:66-76): clouds, search structures, covariances, rotations, scales; filters and z values stay
+void go_swap_source_and_target(void* h) {
+  Oracle* o = (Oracle*)h;
+  std::swap(o->src, o->tgt);
+  std::swap(o->src.filter, o->tgt.filter);
+  std::swap(o->src.has_filter, o->tgt.has_filter);
+  std::swap(o->src.num_trackable, o->tgt.num_trackable);
+  std::swap(o->src.z_values, o->tgt.z_values);
+  o->corr.clear();
+  o->sqd.clear();
+}
+// pcl::Registration::getFitnessScore(max_range): mean squared distance of the transformed source points to their nearest
+// target point over the points whose squared distance is <= max_range; DBL_MAX when there is none.
+double go_get_fitness_score(void* h, double max_range) {
+  Oracle* o = (Oracle*)h;
+  const float* T = o->final_transformation;
+  double sum = 0.0;
+  long nr = 0;
+  std::vector<Cand> nn;
+  for (int i = 0; i < o->src.n; i++) {
+    const float* p = &o->src.xyz[3 * (size_t)i];
+    float q[3];
+    for (int r = 0; r < 3; r++) q[r] = ((T[4 * r] * p[0] + T[4 * r + 1] * p[1]) + T[4 * r + 2] * p[2]) + T[4 * r + 3];
+    o->tgt.tree.search(q, 1, nn);
+    if (!nn.empty() && (double)nn[0].d2 <= max_range) {
+      sum += (double)nn[0].d2;
+      nr++;
+    }
+  }
+  return nr > 0 ? sum / (double)nr : std::numeric_limits<double>::max();
+}
 void go_set_source_covariances_fromqs(void* h, const float* r, const float* s, int n) { Oracle* o = (Oracle*)h; o->covs_from_qs(o->src, r, s, n); }
 void go_set_target_covariances_fromqs(void* h, const float* r, const float* s, int n) { Oracle* o = (Oracle*)h; o->covs_from_qs(o->tgt, r, s, n); }
 int go_align(void* h, const float* guess, float* out) { return ((Oracle*)h)->align(guess, out); }

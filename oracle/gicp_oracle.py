@@ -27,7 +27,9 @@ def lib():
             "go_set_input_source": (None, [vp, vp, i]), "go_set_input_target": (None, [vp, vp, i]),
             "go_set_source_filter": (None, [vp, i, vp, i]), "go_set_target_filter": (None, [vp, i, vp, i]),
             "go_calculate_target_covariance_with_filter": (i, [vp]), "go_calculate_source_covariance": (i, [vp]),
-            "go_calculate_target_covariance": (i, [vp]),
+            "go_calculate_target_covariance": (i, [vp]), "go_calculate_target_covariance_withz": (i, [vp]),
+            "go_set_source_z_values": (None, [vp, vp, i]), "go_set_target_z_values": (None, [vp, vp, i]),
+            "go_swap_source_and_target": (None, [vp]), "go_get_fitness_score": (d, [vp, d]),
             "go_set_source_covariances_fromqs": (None, [vp, vp, vp, i]),
             "go_set_target_covariances_fromqs": (None, [vp, vp, vp, i]),
             "go_align": (i, [vp, vp, vp]), "go_has_converged": (i, [vp]), "go_get_final_hessian": (None, [vp, vp]),
@@ -99,6 +101,23 @@ class FastGICP:
 
     def calculate_target_covariance(self):
         assert self._L.go_calculate_target_covariance(self._h) == 0
+
+    def calculate_target_covariance_withz(self):
+        assert self._L.go_calculate_target_covariance_withz(self._h) == 0
+
+    def set_source_z_values(self, z):
+        z = np.ascontiguousarray(np.asarray(z).reshape(-1), dtype=np.float32)
+        self._L.go_set_source_z_values(self._h, z.ctypes.data, len(z))
+
+    def set_target_z_values(self, z):
+        z = np.ascontiguousarray(np.asarray(z).reshape(-1), dtype=np.float32)
+        self._L.go_set_target_z_values(self._h, z.ctypes.data, len(z))
+
+    def swap_source_and_target(self):
+        self._L.go_swap_source_and_target(self._h)
+
+    def get_fitness_score(self, max_range):
+        return float(self._L.go_get_fitness_score(self._h, float(max_range)))
 
     def set_source_covariances_fromqs(self, r, s):
         r = np.ascontiguousarray(np.asarray(r).reshape(-1), dtype=np.float32)

@@ -146,6 +146,46 @@ def test_reference_fixture_kitti_pair(cuda):
     assert np.abs(pose - k["oracle_pose"]).max() <= 1e-6
 
 
+def test_unused_by_slam_bindings_match_oracle(cuda):
+    """The FastGICP bindings the SLAM scripts never call (main.cpp:169,172,228,246-253): withz covariances, z values,
+    swap_source_and_target, get_fitness_score."""
+    tgt, src, T, g, o = _pair(4000, 3000)
+    z = np.random.default_rng(5).uniform(0.2, 3.0, size=len(tgt)).astype(np.float32)
+    for r in (g, o):
+        r.set_input_target(tgt)
+        r.set_target_z_values(z)
+        r.calculate_target_covariance_withz()
+    assert np.array_equal(g.get_target_rotationsq(), o.get_target_rotationsq())
+    sg, so = g.get_target_scales(), o.get_target_scales()
+    assert np.allclose(sg, so, rtol=2e-7, atol=0)  # pow() may differ in the last place between libm and the device
+    assert _close(g.get_target_covariances(), o.get_target_covariances(), 1e-12)
+    for r in (g, o):
+        r.set_input_source(src)
+    pg, po = g.align(np.eye(4)), o.align(np.eye(4))
+    assert np.abs(pg.astype(np.float64) - po).max() <= 1e-6
+    for rng in (1e-4, 0.01, 1e9):
+        fg, fo = g.get_fitness_score(rng), o.get_fitness_score(rng)
+        assert abs(fg - fo) <= 1e-12 * max(abs(fo), 1e-300), (rng, fg, fo)
+    assert g.get_fitness_score(-1.0) == o.get_fitness_score(-1.0) == np.finfo(np.float64).max
+    # swapped roles: the inverse registration (covariances travel with their clouds)
+    for r in (g, o):
+        r.swap_source_and_target()
+    assert g.source_size() == o.source_size() == len(tgt) and g.target_size() == o.target_size()
+    pg2, po2 = g.align(np.eye(4)), o.align(np.eye(4))
+    assert np.abs(pg2.astype(np.float64) - po2).max() <= 1e-6
+    assert np.abs(pg2.astype(np.float64) @ pg.astype(np.float64) - np.eye(4)).max() < 5e-3
+    cg, dg = g.get_source_correspondence()
+    co, do = o.get_source_correspondence()
+    assert np.array_equal(cg, co) and np.array_equal(dg, do)
+    # withz without z values: an error, not an out-of-bounds read
+    import pygicp
+
+    r = pygicp.FastGICP()
+    r.set_input_target(tgt)
+    with pytest.raises(RuntimeError):
+        r.calculate_target_covariance_withz()
+
+
 def test_edge_cases(cuda):
     import pygicp
     from gs_icp_slam_b200._lib import GsicpError

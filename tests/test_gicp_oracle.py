@@ -217,3 +217,35 @@ def test_golden_c1_and_reference_fixture():
     dR = pose[:3, :3] @ rel[:3, :3].T
     assert np.degrees(np.arccos(min(1.0, (np.trace(dR) - 1) / 2))) < 1.0  # gicp_test.cpp:149
     assert np.array_equal(pose.astype(np.float32), k["oracle_pose"])
+
+
+def test_oracle_withz_swap_fitness():
+    """Bindings unused by the SLAM (main.cpp:169,172,228,246-253) restated in the oracle: consistency checks against numpy."""
+    from oracle import gicp_oracle as G
+
+    tgt, src, T = S.gicp_pair(1500, 1200)
+    z = np.random.default_rng(2).uniform(0.2, 3.0, size=len(tgt)).astype(np.float32)
+    a, b = G.FastGICP(), G.FastGICP()
+    for r in (a, b):
+        r.set_max_correspondence_distance(0.05)
+        r.set_max_knn_distance(99999)
+        r.set_input_target(tgt)
+    a.calculate_target_covariance()
+    b.set_target_z_values(z)
+    b.calculate_target_covariance_withz()
+    zz = np.maximum(1.0, z.astype(np.float64) ** 1.5 * 2.0).astype(np.float32)
+    assert np.array_equal(a.get_target_rotationsq(), b.get_target_rotationsq())
+    assert np.allclose(b.get_target_scales().reshape(-1, 3), a.get_target_scales().reshape(-1, 3) / zz[:, None], rtol=2e-7, atol=0)
+    assert np.array_equal(a.get_target_covariances(), b.get_target_covariances())
+    a.set_input_source(src)
+    pose = a.align(np.eye(4)).astype(np.float32)
+    moved = (src.astype(np.float32) @ pose[:3, :3].T + pose[:3, 3]).astype(np.float32)
+    d2 = ((moved[:, None, :].astype(np.float64) - tgt.astype(np.float32)[None].astype(np.float64)) ** 2).sum(-1).min(1)
+    for rng in (1e-4, 1e9):
+        sel = d2 <= rng
+        assert abs(a.get_fitness_score(rng) - d2[sel].mean()) <= 1e-4 * d2[sel].mean()  # the tree measures distances in float32
+    assert a.get_fitness_score(-1.0) == np.finfo(np.float64).max
+    a.swap_source_and_target()
+    assert a.source_size() == len(tgt) and a.target_size() == len(src)
+    back = a.align(np.eye(4)).astype(np.float64)
+    assert np.abs(back @ pose.astype(np.float64) - np.eye(4)).max() < 5e-3

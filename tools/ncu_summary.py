@@ -1,0 +1,53 @@
+"""Summarise an ncu report (--set full) as text for profiles/:  python tools/ncu_summary.py gpurun_out/x.ncu-rep > profiles/x.txt"""
+import csv
+import io
+import subprocess
+import sys
+
+KEYS = [
+    ("gpu__time_duration.sum", "duration"),
+    ("launch__grid_size", "grid"), ("launch__block_size", "block"), ("launch__registers_per_thread", "regs/thread"),
+    ("launch__shared_mem_per_block_static", "smem static"), ("launch__shared_mem_per_block_dynamic", "smem dynamic"),
+    ("launch__occupancy_limit_registers", "occ limit regs (blocks)"), ("launch__occupancy_limit_shared_mem", "occ limit smem (blocks)"),
+    ("sm__warps_active.avg.pct_of_peak_sustained_active", "achieved occupancy %"),
+    ("smsp__inst_executed.sum", "warp instructions"),
+    ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue slots busy %"),
+    ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "SM throughput %"),
+    ("smsp__thread_inst_executed_per_inst_executed.ratio", "active threads / warp inst"),
+    ("smsp__thread_inst_executed_pred_on_per_inst_executed.ratio", "pred-on threads / warp inst"),
+    ("dram__bytes_read.sum", "DRAM read"), ("dram__bytes_write.sum", "DRAM write"),
+    ("dram__throughput.avg.pct_of_peak_sustained_elapsed", "DRAM throughput %"),
+    ("lts__t_bytes.sum", "L2 bytes"), ("lts__t_sector_hit_rate.pct", "L2 hit rate %"),
+    ("l1tex__t_sector_hit_rate.pct", "L1 hit rate %"),
+    ("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smem bank conflicts"),
+    ("smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "warps stalled long scoreboard / issue"),
+    ("smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio", "warps stalled short scoreboard / issue"),
+    ("smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio", "warps stalled barrier / issue"),
+    ("smsp__average_warps_issue_stalled_wait_per_issue_active.ratio", "warps stalled wait / issue"),
+    ("smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio", "warps stalled math pipe throttle / issue"),
+    ("smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio", "warps stalled mio throttle / issue"),
+    ("smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio", "warps stalled lg throttle / issue"),
+    ("smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio", "warps stalled not selected / issue"),
+    ("smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio", "warps stalled no instruction / issue"),
+    ("smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio", "warps stalled branch resolving / issue"),
+    ("smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio", "warps stalled dispatch stall / issue"),
+    ("smsp__average_warps_issue_stalled_selected_per_issue_active.ratio", "warps stalled selected / issue"),
+]
+
+
+def main(path):
+    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    head, units = rows[0], rows[1]
+    print(f"# {path}: ncu --set full --clock-control none --import-source on (one row per profiled launch)")
+    for r in rows[2:]:
+        d = dict(zip(head, r))
+        u = dict(zip(head, units))
+        print(f"\n== {d['Kernel Name'][:110]}")
+        for k, label in KEYS:
+            if k in d and d[k] != "":
+                print(f"   {label:34s} {d[k]:>16s} {u.get(k, '')}")
+
+
+if __name__ == "__main__":
+    main(sys.argv[1])
