@@ -41,6 +41,9 @@ MAP_SEED = 3
 
 # DRAM bytes per launch from the committed ncu capture of this workload (profiles/r1_ncu_top_kernels.txt)
 NCU_DRAM_BYTES = {"render_backward": 16.73e6, "render_forward": 6.15e6}
+# executed warp instructions per launch from the same capture (smsp__inst_executed.sum): the render kernels are bound by
+# instruction issue (148 SMs x 4 schedulers x 1 warp instruction / clock), not by HBM — reported next to the HBM roofline
+NCU_WARP_INSTRUCTIONS = {"render_backward": 165.6e6, "render_forward": 65.5e6}
 
 
 def parse():
@@ -345,6 +348,10 @@ def cpu_frame(reg, gmap, frames, i, raster):
 def cpu_baseline(gmap, frames, budget_s=20.0):
     from oracle import gicp_oracle as G
 
+    try:  # every host core, also under torchrun (which exports OMP_NUM_THREADS=1)
+        G.set_num_threads(len(os.sched_getaffinity(0)))
+    except Exception:
+        G.set_num_threads(os.cpu_count() or 1)
     reg = G.FastGICP()
     reg.set_max_correspondence_distance(0.03)
     reg.set_max_knn_distance(99999)
@@ -373,6 +380,14 @@ def reference_arm(args, cam, gmap, frames):
         use_gpu = torch.cuda.is_available() and ref_cuda.available()
     except Exception:
         pass
+    try:  # every host core, also under torchrun (which exports OMP_NUM_THREADS=1)
+        G.set_num_threads(len(os.sched_getaffinity(0)))
+    except Exception:
+        G.set_num_threads(os.cpu_count() or 1)
+    try:  # every host core, also under torchrun (which exports OMP_NUM_THREADS=1)
+        G.set_num_threads(len(os.sched_getaffinity(0)))
+    except Exception:
+        G.set_num_threads(os.cpu_count() or 1)
     reg = G.FastGICP()
     reg.set_max_correspondence_distance(0.03)
     reg.set_max_knn_distance(99999)
@@ -544,6 +559,13 @@ def main():
                     "(profiles/r1_ncu_top_kernels.txt); below the algorithmic bytes because the forward pass leaves the tile lists and "
                     "splat records in the 126 MB L2", "peak_source": peak_src, "algorithmic_bytes_per_launch": alg[top],
                     "ms_per_launch": kernels[top]["ms_per_launch"],
+                    "issue": None if top not in NCU_WARP_INSTRUCTIONS else (lambda a, pk: {
+                        "warp_instructions_per_launch": NCU_WARP_INSTRUCTIONS[top], "achieved": a, "peak": pk,
+                        "unit": "G warp-inst/s", "frac": a / pk,
+                        "note": "instruction count from the committed ncu capture of this workload; peak = 148 SMs x 4 "
+                                "schedulers x SM clock"})(
+                        NCU_WARP_INSTRUCTIONS[top] / (kernels[top]["ms_per_launch"] * 1e-3) / 1e9,
+                        148 * 4 * ((clocks or {}).get("sm_mhz") or 1965.0) * 1e6 / 1e9),
                     "render_fwd_bwd_GBps": (alg["render_forward"] + alg["render_backward"]) / 1e9 /
                     ((kernels["render_forward"]["ms_per_launch"] + kernels["render_backward"]["ms_per_launch"]) * 1e-3)
                     if "render_forward" in kernels and "render_backward" in kernels else None}

@@ -55,6 +55,12 @@ def num_threads():
     return lib().go_num_threads()
 
 
+def set_num_threads(n):
+    """OpenMP threads of the oracle (fast_gicp: setNumThreads, fgi:36-44).  torchrun exports OMP_NUM_THREADS=1, so callers
+    that want every host core (bench.py's reference arm) set it explicitly."""
+    lib().go_set_num_threads(int(n))
+
+
 class FastGICP:
     def __init__(self):
         self._L = lib()
