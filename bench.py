@@ -59,8 +59,46 @@ def parse():
                     help="N>1: replicas = one independent SLAM sequence per GPU, no collective (the SLAM loop is sequential in "
                          "time: SURVEY §8e 'replicas only'); shard = ONE sequence, raster tiles + GICP source points sharded over "
                          "the ranks with NCCL all-reduces (pays only at C4/C5 sizes, see tools/bench_large.py)")
+    ap.add_argument("--loss", default="l1", choices=["l1", "ssim_torch", "ssim_fused"],
+                    help="mapper loss: l1 = L1 colour + 0.1 L1 depth in PyTorch ops (default, the workload of every earlier line); "
+                         "ssim_torch = the reference mapper's full loss (masked L1 + 0.2 DSSIM + depth L1, mp_Mapper.py:225-242) in "
+                         "PyTorch ops as the unmodified mapper issues them; ssim_fused = the same loss through "
+                         "gs_icp_slam_b200.loss.mapping_loss (two CUDA kernels)")
     ap.add_argument("--overlap", type=int, default=1, help="1: tracker and mapper on two host threads / CUDA streams (default), 0: back to back")
     return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------
+# the mapper's loss as the reference's PyTorch code evaluates it (caller code, not part of the library)
+# ----------------------------------------------------------------------------------------------
+_WINDOWS = {}
+
+
+def torch_mapper_loss(image, depth, gt_image, gt_depth, lambda_dssim=0.2):
+    """mp_Mapper.py:225-242 with utils/loss_utils.py:17-69: masked L1 + DSSIM (11x11 Gaussian window, sigma 1.5, depthwise
+    conv2d) + 0.1 * L1 of depth / 10, every step a separate PyTorch op like in the reference."""
+    import torch
+    import torch.nn.functional as F
+
+    def l1(x, gt):
+        return torch.where(gt != 0, torch.abs(x - gt), 0.).mean()
+
+    key = (image.device, image.dtype)
+    if key not in _WINDOWS:
+        g = torch.Tensor([math.exp(-(x - 5) ** 2 / float(2 * 1.5 ** 2)) for x in range(11)])
+        g = (g / g.sum()).unsqueeze(1)
+        _WINDOWS[key] = g.mm(g.t()).float().unsqueeze(0).unsqueeze(0).expand(3, 1, 11, 11).contiguous().to(image.device)
+    w = _WINDOWS[key]
+    gt_image = gt_image * (gt_depth > 0.)
+    ll1 = l1(image, gt_image)
+    x = torch.where(gt_image != 0, image, 0.)
+    mu1, mu2 = F.conv2d(x, w, padding=5, groups=3), F.conv2d(gt_image, w, padding=5, groups=3)
+    mu1_sq, mu2_sq, mu12 = mu1.pow(2), mu2.pow(2), mu1 * mu2
+    s1 = F.conv2d(x * x, w, padding=5, groups=3) - mu1_sq
+    s2 = F.conv2d(gt_image * gt_image, w, padding=5, groups=3) - mu2_sq
+    s12 = F.conv2d(x * gt_image, w, padding=5, groups=3) - mu12
+    ssim = (((2 * mu12 + 0.01 ** 2) * (2 * s12 + 0.03 ** 2)) / ((mu1_sq + mu2_sq + 0.01 ** 2) * (s1 + s2 + 0.03 ** 2))).mean()
+    return (1.0 - lambda_dssim) * ll1 + lambda_dssim * (1.0 - ssim) + 0.1 * l1(depth / 10., gt_depth / 10.)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -129,7 +167,7 @@ class ClockSampler:
 # our implementation
 # ----------------------------------------------------------------------------------------------
 class Ours:
-    def __init__(self, cam, gmap, frames, dev, world, rank, shard=False):
+    def __init__(self, cam, gmap, frames, dev, world, rank, shard=False, loss="l1"):
         import torch
 
         import pygicp
@@ -138,6 +176,13 @@ class Ours:
 
         self.torch, self.dev, self.cam, self.frames = torch, dev, cam, frames
         self.world, self.rank = world, rank
+        self.loss_kind = loss
+        if loss == "ssim_fused":
+            from gs_icp_slam_b200 import loss as fused
+
+            self.fused = fused
+        if loss != "l1" and shard:
+            raise SystemExit("--loss ssim_* is not wired for --multi shard (the SSIM window crosses tile shards)")
         self.Settings, self.Rasterizer, self._lib = GaussianRasterizationSettings, GaussianRasterizer, _lib
         self.map_np = gmap
         self.map = {k: torch.from_numpy(v).to(dev).requires_grad_(True) for k, v in gmap.items()}
@@ -232,7 +277,11 @@ class Ours:
         depth, color, radii, is_used = self.Rasterizer(rs)(means3D=m["means3D"], means2D=self.means2D,
                                                            opacities=m["opacities"], shs=m["shs"], scales=m["scales"],
                                                            rotations=m["rotations"])
-        if self.pix_mask is None:
+        if self.loss_kind == "ssim_fused":
+            loss = self.fused.mapping_loss(color, depth, gt_rgb, gt_depth)
+        elif self.loss_kind == "ssim_torch":
+            loss = torch_mapper_loss(color, depth, gt_rgb, gt_depth)
+        elif self.pix_mask is None:
             loss = (color - gt_rgb).abs().mean() + 0.1 * (depth - gt_depth).abs().mean()
         else:
             sh = self.sharding
@@ -384,10 +433,6 @@ def reference_arm(args, cam, gmap, frames):
         G.set_num_threads(len(os.sched_getaffinity(0)))
     except Exception:
         G.set_num_threads(os.cpu_count() or 1)
-    try:  # every host core, also under torchrun (which exports OMP_NUM_THREADS=1)
-        G.set_num_threads(len(os.sched_getaffinity(0)))
-    except Exception:
-        G.set_num_threads(os.cpu_count() or 1)
     reg = G.FastGICP()
     reg.set_max_correspondence_distance(0.03)
     reg.set_max_knn_distance(99999)
@@ -401,22 +446,37 @@ def reference_arm(args, cam, gmap, frames):
             f["d_rgb"], f["d_depth"] = torch.from_numpy(f["rgb"]).to(dev), torch.from_numpy(f["depth"]).to(dev)
             f["d_cam"] = {k: (torch.from_numpy(v).to(dev) if isinstance(v, np.ndarray) else v) for k, v in f["cam"].items()}
 
+    phase = {"tracker_cpu_ms": 0.0, "mapper_ms": 0.0}
+
     def step(i):
         f = frames[i + 1]
+        t_a = time.perf_counter()
         cpu_frame(reg, gmap, frames, i, raster=not use_gpu)
+        t_b = time.perf_counter()
+        phase["tracker_cpu_ms"] += (t_b - t_a) * 1e3
+        step_gpu(f)
+        phase["mapper_ms"] += (time.perf_counter() - t_b) * 1e3
+
+    def step_gpu(f):
         if use_gpu:
             c = f["d_cam"]
             r = ref_cuda.RefRaster(bg, m["means3D"], m["shs"], None, m["opacities"].reshape(-1), m["scales"], m["rotations"],
                                    None, c["viewmatrix"], c["projmatrix"], c["campos"], c["tanfovx"], c["tanfovy"],
                                    cam["H"], cam["W"], 0)
-            gc = torch.sign(r.color - f["d_rgb"]) / r.color.numel()
-            gd = 0.1 * torch.sign(r.depth - f["d_depth"]) / r.depth.numel()
+            if args.loss == "l1":
+                gc = torch.sign(r.color - f["d_rgb"]) / r.color.numel()
+                gd = 0.1 * torch.sign(r.depth - f["d_depth"]) / r.depth.numel()
+            else:  # the reference mapper's full loss, PyTorch ops + autograd
+                col, dep = r.color.detach().requires_grad_(True), r.depth.detach().requires_grad_(True)
+                torch_mapper_loss(col, dep, f["d_rgb"], f["d_depth"]).backward()
+                gc, gd = col.grad, dep.grad
             r.backward(gc, gd)
             torch.cuda.synchronize()
             r.free()
 
     for i in range(args.warmup):
         step(i)
+    phase["tracker_cpu_ms"] = phase["mapper_ms"] = 0.0
     t0 = time.time()
     for i in range(args.warmup, args.warmup + args.steps):
         step(i)
@@ -428,6 +488,7 @@ def reference_arm(args, cam, gmap, frames):
             "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64 (GICP) / f32 (rasterizer)", "data": "synthetic",
             "config": workload_config(args, mapper=mapper),
+            "phase_ms_per_step": {k: v / args.steps for k, v in phase.items()},
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": G.num_threads(), "kind": "port",
                              "sample": f"{args.steps} frames: oracle GICP (fast_gicp restatement, PCL absent) + {mapper}"},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -436,7 +497,9 @@ def reference_arm(args, cam, gmap, frames):
 def workload_config(args, **extra):
     c = {"workload": f"C3 TUM-shape: 640x480 RGB-D, {args.gaussians} Gaussians (seed {MAP_SEED}), 12416 source points/frame, "
                      f"max_corr 0.03, keyframe every {KEYFRAME_EVERY} (target refresh), 1 mapper iteration (raster fwd + "
-                     "L1 colour/depth loss + raster bwd) per frame",
+                     + {"l1": "L1 colour/depth loss", "ssim_torch": "masked L1 + 0.2 DSSIM + depth L1 loss (PyTorch ops)",
+                        "ssim_fused": "masked L1 + 0.2 DSSIM + depth L1 loss (fused CUDA op)"}[getattr(args, "loss", "l1")]
+                     + " + raster bwd) per frame",
          "l2": "256 MiB write between steps, excluded from the per-step CUDA-event time",
          "tracker_mapper": getattr(args, "schedule", {"value": "back_to_back", "e2e": "back_to_back"}),
          "tracker_mapper_note": "back_to_back = one host thread, one stream; concurrent = 2 host threads + 2 CUDA streams like "
@@ -471,7 +534,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     cam, gmap, frames = make_sequence(n_frames, args.gaussians)
     shard = world > 1 and args.multi == "shard"
-    eng = Ours(cam, gmap, frames, dev, world, rank, shard=shard)
+    eng = Ours(cam, gmap, frames, dev, world, rank, shard=shard, loss=args.loss)
     from gs_icp_slam_b200 import _lib
 
     # untimed pre-pass: CUDA module loading, caching-allocator growth and library scratch growth happen here, not in

@@ -32,7 +32,7 @@ void set_error(const char* fmt, ...);
 // CUDA events recorded on the launching stream; totals are resolved when read.  Off by default.
 enum ProfKernel {
   kProfPreprocess = 0, kProfDepthSort, kProfEmit, kProfTileSort, kProfRenderFwd, kProfRenderBwd, kProfGaussBwd,
-  kProfCovariance, kProfLinearize, kProfError, kProfGridBuild, kProfDist2, kProfCount
+  kProfCovariance, kProfLinearize, kProfError, kProfGridBuild, kProfDist2, kProfLossFwd, kProfLossBwd, kProfCount
 };
 extern bool g_prof_on;
 void prof_begin(int k, cudaStream_t s);

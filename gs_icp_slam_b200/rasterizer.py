@@ -62,28 +62,64 @@ def _f32c(t, device):
         return None
     if t.device != device:
         raise ValueError(f"tensor on {t.device}, expected {device}")
+    if t.dtype is torch.float32 and t.is_contiguous():
+        return t
     if t.dtype != torch.float32:
         t = t.float()
     return t.contiguous()
 
 
 class _Buffers:
-    """The three resizable byte buffers (reference: resizeFunctional, rasterize_points.cu:27-33)."""
+    """The three resizable byte buffers (reference: resizeFunctional, rasterize_points.cu:27-33).  One instance per host
+    thread, reused by every call: building a ctypes callback thunk costs more than the call it serves."""
 
-    def __init__(self, device):
-        self.device = device
+    def __init__(self):
+        self.device = None
         self.t = {}
-        self.cbs = []
+        self.cbs = {key: _lib.ALLOC_FN(self._make(key)) for key in ("geom", "binning", "img")}
 
-    def cb(self, key):
+    def _make(self, key):
         def alloc(nbytes, _user):
             t = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
             self.t[key] = t
             return t.data_ptr()
 
-        f = _lib.ALLOC_FN(alloc)
-        self.cbs.append(f)
-        return f
+        return alloc
+
+    def begin(self, device):
+        self.device = device
+        self.t = {}
+        return self
+
+    def cb(self, key):
+        return self.cbs[key]
+
+
+import threading  # noqa: E402
+
+_tls = threading.local()
+
+
+def _buffers(device):
+    b = getattr(_tls, "buffers", None)
+    if b is None:
+        b = _tls.buffers = _Buffers()
+    return b.begin(device)
+
+
+class _on_device:
+    """`with torch.cuda.device(dev)` only when dev is not already current (the context manager costs ~10 us)."""
+
+    def __init__(self, dev):
+        self.ctx = None if (dev.index is None or torch.cuda.current_device() == dev.index) else torch.cuda.device(dev)
+
+    def __enter__(self):
+        if self.ctx is not None:
+            self.ctx.__enter__()
+
+    def __exit__(self, *a):
+        if self.ctx is not None:
+            self.ctx.__exit__(*a)
 
 
 def _make_args(P, D, M, H, W, tanx, tany, scale_mod, prefiltered, debug, bg, means3D, sh, colors, opacity, scales,
@@ -120,7 +156,7 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
         raise RuntimeError("gs_icp_slam_b200 rasterizer: means3D must be a CUDA tensor (no CPU fallback)")
     dev = means3D.device
     P, H, W = means3D.size(0), int(image_height), int(image_width)
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         # The kernels write every element of the four outputs when P > 0 and all tiles are rendered here, so no
         # zero-fill launches are needed (the reference fills them: rasterize_points.cu:65-68).
         alloc = torch.empty if (P != 0 and _tile_shard[0] == 1) else torch.zeros
@@ -128,7 +164,7 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
         out_color = alloc((NUM_CHANNELS, H, W), dtype=torch.float32, device=dev)
         radii = alloc((P,), dtype=torch.int32, device=dev)
         is_used = alloc((P,), dtype=torch.bool, device=dev)
-        bufs = _Buffers(dev)
+        bufs = _buffers(dev)
         rendered = 0
         if P != 0:
             M = sh.size(1) if sh.numel() != 0 else 0
@@ -157,7 +193,7 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
     P = means3D.size(0)
     H, W = dL_dout_color.size(1), dL_dout_color.size(2)
     M = sh.size(1) if sh.numel() != 0 else 0
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         # one zero-filled slab for the eight gradient tensors and the work buffer (one fill launch instead of nine)
         shapes = [(P, 3), (P, 3), (P, NUM_CHANNELS), (P, 1), (P, 6), (P, M, 3), (P, 3), (P, 4)]
         sizes = [int(torch.Size(shp).numel()) for shp in shapes]

@@ -229,6 +229,23 @@ int gsicp_gicp_set_stream(gsicp_gicp*, void* stream);
  * [3]=number of linearize launches, [4]=number of compute_error launches. */
 int gsicp_gicp_last_timing(gsicp_gicp*, double out[5]);
 
+/* ---- fused mapping loss (the caller side of the rasterizer) ----------------------------------
+ * Replaces utils/loss_utils.py:17-20 (l1_loss), :38-69 (ssim/_ssim) and their combination in mp_Mapper.py:225-242:
+ *   loss = (1-lambda) * mean(|image - gt| where gt != 0) + lambda * (1 - mean(ssim(where(gt != 0, image, 0), gt)))
+ *          + depth_weight * mean(|depth/d_max - gt_depth/d_max| where gt_depth != 0)
+ * image, gt_image: [3,H,W] fp32; depth, gt_depth: [1,H,W] fp32 (device).  mask_by_depth != 0 applies
+ * gt_image *= (gt_depth > 0) first (mp_Mapper.py:225-228).  d_out4 receives {loss, L1, SSIM, L1_depth}; d_ssim_map
+ * (optional, [3,H,W]) receives the SSIM map.  d_work: gsicp_mapping_loss_work_bytes(H, W) bytes, kept for backward. */
+size_t gsicp_mapping_loss_work_bytes(int H, int W);
+int gsicp_mapping_loss_forward(int H, int W, const float* d_image, const float* d_depth, const float* d_gt_image,
+                               const float* d_gt_depth, float lambda_dssim, float depth_weight, float d_max,
+                               int mask_by_depth, float* d_out4, float* d_ssim_map, void* d_work, void* stream);
+/* d_grad_loss: device scalar dL/dloss (NULL = 1).  Writes d_grad_image [3,H,W] and d_grad_depth [1,H,W]. */
+int gsicp_mapping_loss_backward(int H, int W, const float* d_image, const float* d_depth, const float* d_gt_image,
+                                const float* d_gt_depth, float lambda_dssim, float depth_weight, float d_max,
+                                int mask_by_depth, const float* d_grad_loss, const void* d_work, float* d_grad_image,
+                                float* d_grad_depth, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -77,6 +77,71 @@ def test_forward_backward_vs_reference_cuda(cuda, P, size, degree, seed):
     ref.free()
 
 
+@pytest.mark.parametrize("active_degree,scale_modifier,size", [(2, 0.7, (250, 190)), (1, 1.6, (96, 64)), (0, 1.0, (17, 33))])
+def test_options_vs_reference_cuda(cuda, active_degree, scale_modifier, size):
+    """SH table larger than the active degree (the SLAM raises active_sh_degree over time), scale_modifier != 1, image
+    sizes that are not multiples of the 16x16 tile, non-zero background."""
+    from gs_icp_slam_b200 import rasterizer as R
+    from oracle import ref_cuda
+
+    if not ref_cuda.available():
+        pytest.skip("oracle/_ref/libref_cuda.so not built")
+    g, cm, t, c, cam = scene_tensors(15000, 40 + active_degree, cuda, sh_degree=3, size=size)
+    W, H = size
+    bg = torch.tensor([0.7, 0.1, 0.4], device=cuda)
+    e = torch.Tensor([])
+    n, depth, color, radii, is_used, geom, binning, img = R.rasterize_gaussians(
+        bg, t["means3D"], e, t["opacities"], t["scales"], t["rotations"], scale_modifier, e, c["viewmatrix"], c["projmatrix"],
+        c["tanfovx"], c["tanfovy"], H, W, t["shs"], active_degree, c["campos"], False, False)
+    ref = ref_cuda.RefRaster(bg, t["means3D"], t["shs"], None, t["opacities"].reshape(-1), t["scales"], t["rotations"], None,
+                             c["viewmatrix"], c["projmatrix"], c["campos"], c["tanfovx"], c["tanfovy"], H, W, active_degree,
+                             scale_modifier=scale_modifier)
+    assert n == ref.num_rendered and n > 0
+    assert torch.equal(radii, ref.radii) and torch.equal(is_used, ref.is_used)
+    pl, rg = R.export_binning(n, H, W, binning, img)
+    rpl, rrg = ref.export()
+    assert torch.equal(rg, rrg) and torch.equal(pl, rpl)
+    assert torch.equal(color, ref.color) and torch.equal(depth, ref.depth)  # bit-identical images
+    gen = torch.Generator(device="cpu").manual_seed(77)
+    gcol = torch.randn((3, H, W), generator=gen).to(cuda)
+    gdep = torch.randn((1, H, W), generator=gen).to(cuda)
+    ours = R.rasterize_gaussians_backward(bg, t["means3D"], radii, e, t["scales"], t["rotations"], scale_modifier, e,
+                                          c["viewmatrix"], c["projmatrix"], c["tanfovx"], c["tanfovy"], gdep, gcol, t["shs"],
+                                          active_degree, c["campos"], geom, n, binning, img, False)
+    rgrad = ref.backward(gcol, gdep)
+    for name, o in zip(["means2D", "colors", "opacity", "means3D", "cov3D", "sh", "scales", "rotations"], ours):
+        assert rel_err(o.cpu().numpy(), rgrad[name].cpu().numpy()) <= 2e-4, name
+    # SH coefficients above the active degree receive no gradient
+    assert float(ours[5][:, (active_degree + 1) ** 2:, :].abs().max()) == 0.0
+    # mark_visible (rasterize_points.cu:208-227) = the near-plane test of the forward pass
+    vis = R.mark_visible(t["means3D"], c["viewmatrix"], c["projmatrix"])
+    assert bool((vis | (radii == 0)).all())
+    ref.free()
+
+
+def test_tile_shards_partition_the_frame(cuda):
+    """Tile sharding on ONE GPU: rendering the shards one after the other reproduces the unsharded frame exactly and the
+    per-shard instance counts add up (the multi-GPU path without the collective)."""
+    from gs_icp_slam_b200 import rasterizer as R
+
+    g, cm, t, c, cam = scene_tensors(20000, 8, cuda, size=(320, 240))
+    bg = torch.tensor([0.2, 0.3, 0.1], device=cuda)
+    full = _ours(t, c, 240, 320, bg)
+    try:
+        total, col, dep = 0, torch.zeros_like(full[2]), torch.zeros_like(full[1])
+        for k in range(3):
+            R.set_tile_shard(3, k)
+            out = _ours(t, c, 240, 320, bg)
+            total += out[0]
+            col += out[2]
+            dep += out[1]
+            assert torch.equal(out[3], full[3])  # radii are computed for every Gaussian on every shard
+    finally:
+        R.set_tile_shard(1, 0)
+    assert total == full[0]
+    assert torch.equal(col, full[2]) and torch.equal(dep, full[1])
+
+
 def test_precomputed_colors_and_cov3d_vs_reference_cuda(cuda):
     """The alternative inputs of GaussianRasterizer.forward: colors_precomp instead of SHs, cov3D_precomp instead of
     scale/rotation (DGR/diff_gaussian_rasterization/__init__.py:189-222)."""

@@ -61,8 +61,17 @@ if which == "c4":
     gen = torch.Generator(device="cpu").manual_seed(5)
     gcol, gdep = torch.randn((3, H, W), generator=gen).to(dev), torch.randn((1, H, W), generator=gen).to(dev)
     R.set_tile_shard(world, rank)
+    cb_time = [0.0, 0]
     if world > 1:
-        R.set_allreduce(sharding.make_raster_allreduce(dev))
+        inner = sharding.make_raster_allreduce(dev)
+
+        def timed_cb(ptr, count, stream):
+            t0 = time.perf_counter()
+            inner(ptr, count, stream)
+            cb_time[0] += time.perf_counter() - t0
+            cb_time[1] = count
+
+        R.set_allreduce(timed_cb)
     mask = sharding.tile_owner_mask(H, W, world, rank, dev)
     rs = GaussianRasterizationSettings(H, W, c["tanfovx"], c["tanfovy"], torch.zeros(3, device=dev), 1.0, c["viewmatrix"],
                                        c["projmatrix"], 0, c["campos"], False, False)
@@ -87,8 +96,27 @@ if which == "c4":
     torch.cuda.synchronize()
     _lib.prof_enable(False)
     kern = {k: round(v[0] / max(v[1], 1) * 1e3, 1) for k, v in _lib.prof_read().items() if v[1]}
+    # phase split (forward / loss + backward), host-timed with a sync on both sides
+    ph = {"fwd": 0.0, "bwd": 0.0}
+    cb_time[0] = 0.0
+    for _ in range(iters):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        depth, color, radii, used = GaussianRasterizer(rs)(means3D=t["means3D"], means2D=m2, opacities=t["opacities"],
+                                                           shs=t["shs"], scales=t["scales"], rotations=t["rotations"])
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        ((color * gcol * mask).sum() + (depth * gdep * mask).sum()).backward()
+        torch.cuda.synchronize()
+        t2 = time.perf_counter()
+        ph["fwd"] += (t1 - t0) * 1e3 / iters
+        ph["bwd"] += (t2 - t1) * 1e3 / iters
+        for k in t:
+            t[k].grad = None
+        m2.grad = None
     if rank == 0:
-        print(json.dumps({"kernels_us": kern}))
+        print(json.dumps({"kernels_us": kern, "phase_ms": ph, "allreduce_cb_ms": cb_time[0] * 1e3 / iters,
+                          "allreduce_floats": cb_time[1]}))
         print(json.dumps({"config": "C4 1280x960, 1M Gaussians, raster fwd+bwd, tile-sharded", "n_gpus": world, "ms_per_iter": ms,
                           "iters_per_s": 1e3 / ms, "tile_instances_this_rank": info["R"]}))
 else:
