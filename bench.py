@@ -6,8 +6,10 @@ One "step" = one SLAM frame of the two hot paths, in the order the reference's p
             -> get_source_correspondence; every 5th frame is a tracking keyframe: get_source_rotationsq/scales,
             set_input_target(map points) + set_target_covariances_fromqs(map rotations, scales)
   mapper   (mp_Mapper.py:219-242, one training iteration): GaussianRasterizer forward on the 300k-Gaussian map at the
-            frame's camera -> L1(colour) + 0.1 L1(depth) against the frame's RGB-D -> backward through the rasterizer
-            (loss arithmetic is a few PyTorch element-wise ops; Adam is outside the hot path).
+            frame's camera -> the mapper's loss against the frame's RGB-D (masked L1 + 0.2 DSSIM + 0.1 depth L1; ours: the
+            fused op gs_icp_slam_b200.loss.mapping_loss, reference arm: the reference's PyTorch ops; `loss_variants` in the
+            JSON line lists our frame rate with the PyTorch formulation too) -> backward through the rasterizer.
+            Adam is outside the hot path.
 Workload = BASELINE config C3: 640x480, fx 517.3 ..., downsample 5, max_corr 0.03, 300 000 Gaussians (seed 3).
 
 Printed JSON (one line, rank 0): `value` = frames/s with every input already resident in HBM; `e2e.value` = frames/s
@@ -28,7 +30,12 @@ import sys
 import threading
 import time
 
-import numpy as np
+# The CPU legs (reference arm, cpu_baseline) run OpenMP teams of one thread per logical CPU next to a thread that drives the
+# GPU.  libgomp's default is to spin after every parallel region; on a shared host that starves the GPU-driving thread and the
+# teams themselves (measured on one box: 1.5 frames/s spinning vs 12.7 passive, same run).  Must be set before libgomp loads.
+os.environ.setdefault("OMP_WAIT_POLICY", "passive")
+
+import numpy as np  # noqa: E402
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -48,6 +55,7 @@ NCU_WARP_INSTRUCTIONS = {"render_backward": 165.6e6, "render_forward": 65.5e6}
 
 def parse():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--no-variants", action="store_true", help="skip the loss_variants passes")
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
@@ -59,13 +67,17 @@ def parse():
                     help="N>1: replicas = one independent SLAM sequence per GPU, no collective (the SLAM loop is sequential in "
                          "time: SURVEY §8e 'replicas only'); shard = ONE sequence, raster tiles + GICP source points sharded over "
                          "the ranks with NCCL all-reduces (pays only at C4/C5 sizes, see tools/bench_large.py)")
-    ap.add_argument("--loss", default="l1", choices=["l1", "ssim_torch", "ssim_fused"],
-                    help="mapper loss: l1 = L1 colour + 0.1 L1 depth in PyTorch ops (default, the workload of every earlier line); "
-                         "ssim_torch = the reference mapper's full loss (masked L1 + 0.2 DSSIM + depth L1, mp_Mapper.py:225-242) in "
-                         "PyTorch ops as the unmodified mapper issues them; ssim_fused = the same loss through "
-                         "gs_icp_slam_b200.loss.mapping_loss (two CUDA kernels)")
+    ap.add_argument("--loss", default="ssim", choices=["ssim", "ssim_fused", "ssim_torch", "l1"],
+                    help="mapper loss.  ssim (default) = the reference mapper's loss (masked L1 + 0.2 DSSIM + depth L1, "
+                         "mp_Mapper.py:225-242): our arm evaluates it with gs_icp_slam_b200.loss.mapping_loss (two CUDA kernels, "
+                         "= ssim_fused), the reference arm with the reference's PyTorch ops (= ssim_torch); our line also reports "
+                         "the other variants under loss_variants.  l1 = L1 colour + 0.1 L1 depth in PyTorch ops (the simplified "
+                         "workload of the first bench lines of this round)")
     ap.add_argument("--overlap", type=int, default=1, help="1: tracker and mapper on two host threads / CUDA streams (default), 0: back to back")
-    return ap.parse_args()
+    a = ap.parse_args()
+    if a.loss == "ssim":
+        a.loss = "ssim_torch" if a.impl == "reference" else "ssim_fused"
+    return a
 
 
 # ----------------------------------------------------------------------------------------------
@@ -176,13 +188,12 @@ class Ours:
 
         self.torch, self.dev, self.cam, self.frames = torch, dev, cam, frames
         self.world, self.rank = world, rank
-        self.loss_kind = loss
-        if loss == "ssim_fused":
-            from gs_icp_slam_b200 import loss as fused
+        from gs_icp_slam_b200 import loss as fused
 
-            self.fused = fused
+        self.fused = fused
+        self.loss_kind = loss
         if loss != "l1" and shard:
-            raise SystemExit("--loss ssim_* is not wired for --multi shard (the SSIM window crosses tile shards)")
+            raise SystemExit("--loss ssim* is not wired for --multi shard (the SSIM window crosses tile shards); use --loss l1")
         self.Settings, self.Rasterizer, self._lib = GaussianRasterizationSettings, GaussianRasterizer, _lib
         self.map_np = gmap
         self.map = {k: torch.from_numpy(v).to(dev).requires_grad_(True) for k, v in gmap.items()}
@@ -201,6 +212,7 @@ class Ours:
             f["h_rgb"] = torch.from_numpy(f["rgb"]).pin_memory()
             f["h_depth"] = torch.from_numpy(f["depth"]).pin_memory()
             f["d_cam"] = {k: (torch.from_numpy(v).to(dev) if isinstance(v, np.ndarray) else v) for k, v in f["cam"].items()}
+        self.copy_stream = None
         self.stage_rgb = torch.empty((3, H, W), device=dev)
         self.stage_depth = torch.empty((1, H, W), device=dev)
         self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -222,6 +234,9 @@ class Ours:
         self.pool = None
         self.stats = dict(R=0, V=0, n_src=0, n_corr=0, n_tgt=0, frames=0, h2d=0, d2h=0)
         self.refresh_target(resident=True)
+
+    def set_loss(self, kind):
+        self.loss_kind = kind
 
     def refresh_target(self, resident):
         m = self.map
@@ -267,8 +282,16 @@ class Ours:
         if resident:
             gt_rgb, gt_depth = f["d_rgb"], f["d_depth"]
         else:
-            self.stage_rgb.copy_(f["h_rgb"], non_blocking=True)
-            self.stage_depth.copy_(f["h_depth"], non_blocking=True)
+            # pinned host frame -> device on a copy stream, overlapped with the rasterizer forward; the loss waits for it
+            if self.copy_stream is None:
+                self.copy_stream = torch.cuda.Stream(device=self.dev)
+                self.copy_done = torch.cuda.Event()
+            cur = torch.cuda.current_stream(self.dev)
+            self.copy_stream.wait_stream(cur)  # the previous frame's loss has finished reading the staging buffers
+            with torch.cuda.stream(self.copy_stream):
+                self.stage_rgb.copy_(f["h_rgb"], non_blocking=True)
+                self.stage_depth.copy_(f["h_depth"], non_blocking=True)
+                self.copy_done.record()
             gt_rgb, gt_depth = self.stage_rgb, self.stage_depth
             st["h2d"] += f["h_rgb"].numel() * 4 + f["h_depth"].numel() * 4
         c, cam, m = f["d_cam"], self.cam, self.map
@@ -277,6 +300,8 @@ class Ours:
         depth, color, radii, is_used = self.Rasterizer(rs)(means3D=m["means3D"], means2D=self.means2D,
                                                            opacities=m["opacities"], shs=m["shs"], scales=m["scales"],
                                                            rotations=m["rotations"])
+        if not resident:
+            torch.cuda.current_stream(self.dev).wait_event(self.copy_done)
         if self.loss_kind == "ssim_fused":
             loss = self.fused.mapping_loss(color, depth, gt_rgb, gt_depth)
         elif self.loss_kind == "ssim_torch":
@@ -497,9 +522,11 @@ def reference_arm(args, cam, gmap, frames):
 def workload_config(args, **extra):
     c = {"workload": f"C3 TUM-shape: 640x480 RGB-D, {args.gaussians} Gaussians (seed {MAP_SEED}), 12416 source points/frame, "
                      f"max_corr 0.03, keyframe every {KEYFRAME_EVERY} (target refresh), 1 mapper iteration (raster fwd + "
-                     + {"l1": "L1 colour/depth loss", "ssim_torch": "masked L1 + 0.2 DSSIM + depth L1 loss (PyTorch ops)",
-                        "ssim_fused": "masked L1 + 0.2 DSSIM + depth L1 loss (fused CUDA op)"}[getattr(args, "loss", "l1")]
+                     + ("L1 colour/depth loss" if getattr(args, "loss", "l1") == "l1" else
+                        "the reference mapper's loss: masked L1 + 0.2 DSSIM + 0.1 depth L1, mp_Mapper.py:225-242")
                      + " + raster bwd) per frame",
+         "loss_impl": {"l1": "PyTorch ops", "ssim_torch": "PyTorch ops (utils/loss_utils.py formulation)",
+                       "ssim_fused": "gs_icp_slam_b200.loss.mapping_loss (2 CUDA kernels)"}[getattr(args, "loss", "l1")],
          "l2": "256 MiB write between steps, excluded from the per-step CUDA-event time",
          "tracker_mapper": getattr(args, "schedule", {"value": "back_to_back", "e2e": "back_to_back"}),
          "tracker_mapper_note": "back_to_back = one host thread, one stream; concurrent = 2 host threads + 2 CUDA streams like "
@@ -574,6 +601,22 @@ def main():
     _, launches, st_res = sched[best_res]["res"]
     _, _, st_e2e = sched[best_e2e]["e2e"]
     args.schedule = {"value": best_res, "e2e": best_e2e}
+    # the other formulations of the mapper's loss, same schedule as the headline leg, K steps each
+    variants = {}
+    if not args.no_variants and not shard:
+        for kind in ("ssim_fused", "ssim_torch", "l1"):
+            if kind == args.loss:
+                continue
+            eng.set_loss(kind)
+            r = {}
+            for leg, mode, resident in (("value", best_res, True), ("e2e", best_e2e, False)):
+                eng.enable_overlap(mode == "concurrent")
+                eng.run(min(args.steps, 5), 1, resident=resident)
+                t, _, _ = eng.run(args.steps, args.warmup, resident=resident)
+                r[leg] = (1 if shard else world) * args.steps / (max_over_ranks(t) * 1e-3)
+            variants[kind] = r
+        eng.enable_overlap(False)
+        eng.set_loss(args.loss)
     prof, st_p = {}, st_res
     if not args.no_roofline:
         _, _, st_p = eng.run(args.steps, args.warmup, resident=True, profile=True)
@@ -648,6 +691,9 @@ def main():
            "e2e": {"value": seqs * K / (t_e2e * 1e-3), "unit": "frames/s", "ms_per_step": t_e2e / K,
                    "h2d_bytes_per_step": st_e2e["h2d"] / K, "d2h_bytes_per_step": st_e2e["d2h"] / K},
            "roofline": roofline, "kernels": kernels,
+           "loss_variants": dict(variants, **{args.loss: {"value": seqs * K / (t_res * 1e-3), "e2e": seqs * K / (t_e2e * 1e-3)}},
+                                 note="ssim_fused = mapper loss through gs_icp_slam_b200.loss (headline when --loss ssim); ssim_torch = "
+                                      "the same loss in the reference's PyTorch ops (unmodified mp_Mapper.py); l1 = simplified L1 loss"),
            "schedules": {m: {"value": seqs * K / (sched[m]["t_res"] * 1e-3), "e2e": seqs * K / (sched[m]["t_e2e"] * 1e-3),
                              "value_ms_p50_max": [float(np.median(sched[m]["res_times"])), float(np.max(sched[m]["res_times"]))],
                              "e2e_ms_p50_max": [float(np.median(sched[m]["e2e_times"])), float(np.max(sched[m]["e2e_times"]))]}
