@@ -60,6 +60,7 @@ class _RasterizeGaussians(torch.autograd.Function):
             raise
         ctx.raster_settings = rs
         ctx.num_rendered = n
+        ctx.set_materialize_grads(False)  # no zero tensors for the radii / is_used slots (backward handles None)
         ctx.save_for_backward(colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, sh, geom, binning, img)
         ctx.mark_non_differentiable(radii, is_used)
         return depth, color, radii, is_used

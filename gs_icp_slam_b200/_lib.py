@@ -120,7 +120,7 @@ _sig("gsicp_gicp_compute_error", i32, [vp, vp, vp])
 _sig("gsicp_gicp_set_shard", i32, [vp, i32, i32, ALLREDUCE_FN, vp])
 _sig("gsicp_gicp_set_stream", i32, [vp, vp])
 _sig("gsicp_mapping_loss_work_bytes", C.c_size_t, [i32, i32])
-_sig("gsicp_mapping_loss_forward", i32, [i32, i32, vp, vp, vp, vp, C.c_float, C.c_float, C.c_float, i32, vp, vp, vp, vp])
+_sig("gsicp_mapping_loss_forward", i32, [i32, i32, vp, vp, vp, vp, C.c_float, C.c_float, C.c_float, i32, vp, vp, vp, vp, vp])
 _sig("gsicp_mapping_loss_backward", i32, [i32, i32, vp, vp, vp, vp, C.c_float, C.c_float, C.c_float, i32, vp, vp, vp, vp, vp])
 _sig("gsicp_gicp_last_timing", i32, [vp, vp])
 

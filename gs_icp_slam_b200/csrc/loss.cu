@@ -41,7 +41,8 @@ struct LossArgs {
   float* ssim_map;        // optional [3][H][W]
   double* partial;        // [blocks][3]: sum ssim, sum masked |x-gt|, sum masked depth L1
   unsigned int* counter;
-  float* out;             // [4]: loss, L1, SSIM, L1 depth
+  float* loss;            // scalar
+  float* parts;           // optional [3]: L1, SSIM, L1 depth
 };
 
 __device__ __forceinline__ float block_sum(float v, float* s_red) {
@@ -180,10 +181,12 @@ mapping_loss_forward_kernel(LossArgs a, LossWindow win) {
         for (int w = 0; w < 8; w++) t[k] += s_acc[k][w];
       const double n3 = 3.0 * (double)a.H * (double)a.W, n1 = (double)a.H * (double)a.W;
       const float ssim = (float)(t[0] / n3), l1 = (float)(t[1] / n3), ld = (float)(t[2] / n1);
-      a.out[0] = (1.f - a.lambda_dssim) * l1 + a.lambda_dssim * (1.f - ssim) + a.depth_weight * ld;
-      a.out[1] = l1;
-      a.out[2] = ssim;
-      a.out[3] = ld;
+      *a.loss = (1.f - a.lambda_dssim) * l1 + a.lambda_dssim * (1.f - ssim) + a.depth_weight * ld;
+      if (a.parts) {
+        a.parts[0] = l1;
+        a.parts[1] = ssim;
+        a.parts[2] = ld;
+      }
       *a.counter = 0u;  // ready for the next call
     }
   }
@@ -309,8 +312,8 @@ static inline char* loss_partial_ptr(void* work, int H, int W) {
 
 int gsicp_mapping_loss_forward(int H, int W, const float* d_image, const float* d_depth, const float* d_gt_image,
                                const float* d_gt_depth, float lambda_dssim, float depth_weight, float d_max,
-                               int mask_by_depth, float* d_out4, float* d_ssim_map, void* d_work, void* stream_) {
-  if (H <= 0 || W <= 0 || !d_image || !d_depth || !d_gt_image || !d_gt_depth || !d_out4 || !d_work || !(d_max > 0.f)) {
+                               int mask_by_depth, float* d_loss, float* d_parts3, float* d_ssim_map, void* d_work, void* stream_) {
+  if (H <= 0 || W <= 0 || !d_image || !d_depth || !d_gt_image || !d_gt_depth || !d_loss || !d_work || !(d_max > 0.f)) {
     set_error("gsicp_mapping_loss_forward: bad arguments");
     return GSICP_EINVAL;
   }
@@ -324,7 +327,8 @@ int gsicp_mapping_loss_forward(int H, int W, const float* d_image, const float* 
   char* p = loss_partial_ptr(d_work, H, W);
   a.partial = (double*)p;
   a.counter = (unsigned int*)(p + (size_t)grid.x * grid.y * grid.z * 3 * sizeof(double));
-  a.out = d_out4;
+  a.loss = d_loss;
+  a.parts = d_parts3;
   GSICP_CUDA(cudaMemsetAsync(a.counter, 0, sizeof(unsigned int), stream));  // the work buffer is caller-allocated, not zeroed
   static const LossWindow win = make_window();
   ProfScope ps(kProfLossFwd, stream);

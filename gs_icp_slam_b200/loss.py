@@ -37,17 +37,19 @@ class _MappingLoss(torch.autograd.Function):
             raise RuntimeError("image / depth / ground-truth shapes do not match")
         dev = img.device
         work = torch.empty(int(lib.gsicp_mapping_loss_work_bytes(H, W)), dtype=torch.uint8, device=dev)
-        out4 = torch.empty(4, dtype=torch.float32, device=dev)
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        parts = torch.empty(3, dtype=torch.float32, device=dev)
         smap = torch.empty_like(img) if want_map else None
         stream = torch.cuda.current_stream(dev).cuda_stream
         check(lib.gsicp_mapping_loss_forward(H, W, img.data_ptr(), dep.data_ptr(), gti.data_ptr(), gtd.data_ptr(),
                                              float(lambda_dssim), float(depth_weight), float(d_max), int(bool(mask_by_depth)),
-                                             out4.data_ptr(), smap.data_ptr() if want_map else None, work.data_ptr(), stream),
+                                             loss.data_ptr(), parts.data_ptr(), smap.data_ptr() if want_map else None,
+                                             work.data_ptr(), stream),
               "gsicp_mapping_loss_forward")
         ctx.save_for_backward(img, dep, gti, gtd, work)
         ctx.cfg = (H, W, float(lambda_dssim), float(depth_weight), float(d_max), int(bool(mask_by_depth)))
         ctx.in_shapes = (image.shape, depth.shape)
-        loss, parts = out4[:1].view(()), out4[1:]  # disjoint slices: [loss] and [Ll1, ssim, Ll1_depth]
+        ctx.set_materialize_grads(False)  # no zero tensors for the non-differentiable outputs
         if want_map:
             ctx.mark_non_differentiable(parts, smap)
             return loss, parts, smap
@@ -56,10 +58,14 @@ class _MappingLoss(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_loss, *_unused):
+        if grad_loss is None:
+            return (None,) * 9
         img, dep, gti, gtd, work = ctx.saved_tensors
         H, W, lam, dw, dmax, mbd = ctx.cfg
         g_img, g_dep = torch.empty_like(img), torch.empty_like(dep)
-        gl = grad_loss.to(device=img.device, dtype=torch.float32).contiguous()
+        gl = grad_loss
+        if gl.dtype is not torch.float32 or gl.device != img.device or not gl.is_contiguous():
+            gl = gl.to(device=img.device, dtype=torch.float32).contiguous()
         stream = torch.cuda.current_stream(img.device).cuda_stream
         check(lib.gsicp_mapping_loss_backward(H, W, img.data_ptr(), dep.data_ptr(), gti.data_ptr(), gtd.data_ptr(), lam, dw, dmax,
                                               mbd, gl.data_ptr(), work.data_ptr(), g_img.data_ptr(), g_dep.data_ptr(), stream),

@@ -122,23 +122,35 @@ class _on_device:
             self.ctx.__exit__(*a)
 
 
-def _make_args(P, D, M, H, W, tanx, tany, scale_mod, prefiltered, debug, bg, means3D, sh, colors, opacity, scales,
-               rotations, cov3D, view, proj, campos):
-    a = RasterArgs()
+def _arg(t, device):
+    """(tensor to keep alive, device pointer) of an optional float32 input; (None, None) for the reference's 'not provided'
+    empty tensor.  Fast path: float32 + contiguous tensors are passed through untouched."""
+    if t is None:
+        return None, None
+    if t.dtype is not torch.float32 or not t.is_contiguous():
+        if t.numel() == 0:
+            return None, None
+        t = t.float().contiguous()
+    elif t.numel() == 0:
+        return None, None
+    if t.device != device:
+        raise ValueError(f"tensor on {t.device}, expected {device}")
+    return t, t.data_ptr()
+
+
+def _args_struct():
+    a = getattr(_tls, "args", None)
+    if a is None:
+        a = _tls.args = RasterArgs()
+    return a
+
+
+def _fill_args(a, P, D, M, H, W, tanx, tany, scale_mod, prefiltered, debug, ptrs):
     a.P, a.D, a.M, a.width, a.height = P, D, M, W, H
     a.tan_fovx, a.tan_fovy, a.scale_modifier = tanx, tany, scale_mod
     a.prefiltered, a.debug = int(bool(prefiltered)), int(bool(debug))
-    a.d_background = _ptr(bg)
-    a.d_means3D = _ptr(means3D)
-    a.d_shs = _ptr(sh)
-    a.d_colors_precomp = _ptr(colors)
-    a.d_opacities = _ptr(opacity)
-    a.d_scales = _ptr(scales)
-    a.d_rotations = _ptr(rotations)
-    a.d_cov3D_precomp = _ptr(cov3D)
-    a.d_viewmatrix = _ptr(view)
-    a.d_projmatrix = _ptr(proj)
-    a.d_campos = _ptr(campos)
+    (a.d_background, a.d_means3D, a.d_shs, a.d_colors_precomp, a.d_opacities, a.d_scales, a.d_rotations, a.d_cov3D_precomp,
+     a.d_viewmatrix, a.d_projmatrix, a.d_campos) = ptrs
     a.tile_shard_count, a.tile_shard_index = _tile_shard
     return a
 
@@ -168,19 +180,22 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
         rendered = 0
         if P != 0:
             M = sh.size(1) if sh.numel() != 0 else 0
-            keep = [_f32c(x, dev) for x in (background, means3D, sh, colors, opacity, scales, rotations, cov3D_precomp,
-                                            viewmatrix, projmatrix, campos)]
-            bg, m3, shc, col, opa, sc, rot, cov, view, proj, cam = keep
-            args = _make_args(P, int(degree), M, H, W, float(tan_fovx), float(tan_fovy), float(scale_modifier),
-                              prefiltered, debug, bg, m3, shc, col, opa, sc, rot, cov, view, proj, cam)
+            keep, ptrs = zip(*[_arg(x, dev) for x in (background, means3D, sh, colors, opacity, scales, rotations,
+                                                        cov3D_precomp, viewmatrix, projmatrix, campos)])
+            args = _fill_args(_args_struct(), P, int(degree), M, H, W, float(tan_fovx), float(tan_fovy), float(scale_modifier),
+                              prefiltered, debug, ptrs)
             stream = torch.cuda.current_stream(dev).cuda_stream
             rendered = check(
                 lib.gsicp_raster_forward(C.byref(args), out_color.data_ptr(), out_depth.data_ptr(), radii.data_ptr(),
                                          is_used.data_ptr(), bufs.cb("geom"), bufs.cb("binning"), bufs.cb("img"), None,
                                          stream), "gsicp_raster_forward")
-        empty = torch.empty(0, dtype=torch.uint8, device=dev)
-        return (rendered, out_depth, out_color, radii, is_used, bufs.t.get("geom", empty), bufs.t.get("binning", empty),
-                bufs.t.get("img", empty))
+            del keep
+        t = bufs.t
+        empty = None
+        if len(t) != 3:
+            empty = torch.empty(0, dtype=torch.uint8, device=dev)
+        return (rendered, out_depth, out_color, radii, is_used, t.get("geom", empty), t.get("binning", empty),
+                t.get("img", empty))
 
 
 def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rotations, scale_modifier, cov3D_precomp,
@@ -194,33 +209,33 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
     H, W = dL_dout_color.size(1), dL_dout_color.size(2)
     M = sh.size(1) if sh.numel() != 0 else 0
     with _on_device(dev):
-        # one zero-filled slab for the eight gradient tensors and the work buffer (one fill launch instead of nine)
-        shapes = [(P, 3), (P, 3), (P, NUM_CHANNELS), (P, 1), (P, 6), (P, M, 3), (P, 3), (P, 4)]
-        sizes = [int(torch.Size(shp).numel()) for shp in shapes]
-        pad = lambda n: (n + 3) // 4 * 4  # keep every view 16-byte aligned
+        # One zero-filled slab for the eight gradient tensors and the work buffer (one fill launch instead of nine).  The
+        # kernels are launched from raw offsets into it; the tensor views are made afterwards, while the GPU is busy.
+        sizes = (3 * P, 3 * P, NUM_CHANNELS * P, P, 6 * P, 3 * M * P, 3 * P, 4 * P)
+        offs, off = [], 0
+        for n in sizes:
+            offs.append(off)
+            off += (n + 3) // 4 * 4  # keep every view 16-byte aligned
         work_n = (int(lib.gsicp_raster_backward_work_bytes(P)) // 4) if P != 0 else 0
-        slab = torch.zeros(sum(pad(n) for n in sizes) + work_n, dtype=torch.float32, device=dev)
-        views, off = [], 0
-        for shp, n in zip(shapes, sizes):
-            views.append(slab[off:off + n].view(shp))
-            off += pad(n)
-        dL_dmeans3D, dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations = views
+        slab = torch.zeros(off + work_n, dtype=torch.float32, device=dev)
         if P != 0:
-            work = slab[off:off + work_n]
-            keep = [_f32c(x, dev) for x in (background, means3D, sh, colors, None, scales, rotations, cov3D_precomp,
-                                            viewmatrix, projmatrix, campos, dL_dout_color, dL_dout_depth)]
-            bg, m3, shc, col, _, sc, rot, cov, view, proj, cam, gcol, gdep = keep
-            args = _make_args(P, int(degree), M, H, W, float(tan_fovx), float(tan_fovy), float(scale_modifier), False,
-                              debug, bg, m3, shc, col, None, sc, rot, cov, view, proj, cam)
+            base = slab.data_ptr()
+            p3d, p2d, pcol, popa, pcov, psh, psc, prot = (base + 4 * o for o in offs)
+            keep, ptrs = zip(*[_arg(x, dev) for x in (background, means3D, sh, colors, None, scales, rotations, cov3D_precomp,
+                                                        viewmatrix, projmatrix, campos, dL_dout_color, dL_dout_depth)])
+            args = _fill_args(_args_struct(), P, int(degree), M, H, W, float(tan_fovx), float(tan_fovy), float(scale_modifier),
+                              False, debug, ptrs[:11])
             stream = torch.cuda.current_stream(dev).cuda_stream
-            radii_c = radii.contiguous()
+            radii_c = radii if radii.is_contiguous() else radii.contiguous()
             check(
                 lib.gsicp_raster_backward(C.byref(args), int(R), radii_c.data_ptr(), geomBuffer.data_ptr(),
-                                          binningBuffer.data_ptr(), imageBuffer.data_ptr(), gcol.data_ptr(),
-                                          gdep.data_ptr(), dL_dmeans2D.data_ptr(), dL_dcolors.data_ptr(),
-                                          dL_dopacity.data_ptr(), dL_dmeans3D.data_ptr(), dL_dcov3D.data_ptr(),
-                                          _ptr(dL_dsh), dL_dscales.data_ptr(), dL_drotations.data_ptr(),
-                                          work.data_ptr(), stream), "gsicp_raster_backward")
+                                          binningBuffer.data_ptr(), imageBuffer.data_ptr(), ptrs[11], ptrs[12], p2d, pcol, popa,
+                                          p3d, pcov, psh if M != 0 else None, psc, prot, base + 4 * off, stream),
+                "gsicp_raster_backward")
+            del keep
+        shapes = ((P, 3), (P, 3), (P, NUM_CHANNELS), (P, 1), (P, 6), (P, M, 3), (P, 3), (P, 4))
+        dL_dmeans3D, dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations = (
+            slab[o:o + n].view(shp) for o, n, shp in zip(offs, sizes, shapes))
         return dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations
 
 

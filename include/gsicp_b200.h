@@ -234,12 +234,14 @@ int gsicp_gicp_last_timing(gsicp_gicp*, double out[5]);
  *   loss = (1-lambda) * mean(|image - gt| where gt != 0) + lambda * (1 - mean(ssim(where(gt != 0, image, 0), gt)))
  *          + depth_weight * mean(|depth/d_max - gt_depth/d_max| where gt_depth != 0)
  * image, gt_image: [3,H,W] fp32; depth, gt_depth: [1,H,W] fp32 (device).  mask_by_depth != 0 applies
- * gt_image *= (gt_depth > 0) first (mp_Mapper.py:225-228).  d_out4 receives {loss, L1, SSIM, L1_depth}; d_ssim_map
+ * gt_image *= (gt_depth > 0) first (mp_Mapper.py:225-228).  d_loss receives the scalar, d_parts3 (optional) {L1, SSIM,
+ * L1_depth}; d_ssim_map
  * (optional, [3,H,W]) receives the SSIM map.  d_work: gsicp_mapping_loss_work_bytes(H, W) bytes, kept for backward. */
 size_t gsicp_mapping_loss_work_bytes(int H, int W);
 int gsicp_mapping_loss_forward(int H, int W, const float* d_image, const float* d_depth, const float* d_gt_image,
                                const float* d_gt_depth, float lambda_dssim, float depth_weight, float d_max,
-                               int mask_by_depth, float* d_out4, float* d_ssim_map, void* d_work, void* stream);
+                               int mask_by_depth, float* d_loss, float* d_parts3, float* d_ssim_map, void* d_work,
+                               void* stream);
 /* d_grad_loss: device scalar dL/dloss (NULL = 1).  Writes d_grad_image [3,H,W] and d_grad_depth [1,H,W]. */
 int gsicp_mapping_loss_backward(int H, int W, const float* d_image, const float* d_depth, const float* d_gt_image,
                                 const float* d_gt_depth, float lambda_dssim, float depth_weight, float d_max,
