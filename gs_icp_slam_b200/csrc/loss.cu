@@ -24,6 +24,7 @@ constexpr int kLossTile = 16;
 constexpr int kWin = 11;
 constexpr int kHalo = kWin / 2;
 constexpr int kLossIn = kLossTile + 2 * kHalo;  // 26
+constexpr int kLossFwdCtas = 148 * 8;            // forward grid: persistent CTAs walking (tile, channel) items
 
 struct LossWindow {
   float w[kWin];
@@ -59,29 +60,36 @@ __device__ __forceinline__ float block_sum(float v, float* s_red) {
   return r;  // valid in thread 0
 }
 
-// grid (tiles_x, tiles_y, 4): z = 0..2 colour channels (SSIM + L1), z = 3 the depth image (L1 only).
+// Work item = (16x16 pixel tile, z) with z = 0..2 the colour channels (SSIM + L1) and z = 3 the depth image (L1 only).
+// The grid is a few CTAs per SM; each CTA walks items with a grid stride and keeps its three partial sums in registers,
+// so the cross-CTA reduction (one fence + one same-address atomic per CTA) is paid ~600 times, not once per tile.
 __global__ void __launch_bounds__(kLossTile * kLossTile)
 mapping_loss_forward_kernel(LossArgs a, LossWindow win) {
   __shared__ float sx[kLossIn][kLossIn], sy[kLossIn][kLossIn];
   __shared__ float sh[5][kLossIn][kLossTile];
   __shared__ float s_red[8];
   const int tx = threadIdx.x % kLossTile, ty = threadIdx.x / kLossTile;
-  const int x0 = blockIdx.x * kLossTile, y0 = blockIdx.y * kLossTile;
-  const int px = x0 + tx, py = y0 + ty;
-  const bool inside = px < a.W && py < a.H;
-  const int z = blockIdx.z;
+  const int tiles_x = (a.W + kLossTile - 1) / kLossTile, tiles_y = (a.H + kLossTile - 1) / kLossTile;
+  const int items = tiles_x * tiles_y * 4;
   const size_t plane = (size_t)a.H * a.W;
   float s_ssim = 0.f, s_l1 = 0.f, s_d = 0.f;
 
-  if (z == 3) {
-    if (inside) {
-      const float gd = a.gt_depth[(size_t)py * a.W + px] * a.inv_dmax;
-      const float d = a.depth[(size_t)py * a.W + px] * a.inv_dmax;
-      s_d = (gd != 0.f) ? fabsf(d - gd) : 0.f;
+  for (int item = blockIdx.x; item < items; item += gridDim.x) {
+    const int z = item / (tiles_x * tiles_y), t = item % (tiles_x * tiles_y);
+    const int x0 = (t % tiles_x) * kLossTile, y0 = (t / tiles_x) * kLossTile;
+    const int px = x0 + tx, py = y0 + ty;
+    const bool inside = px < a.W && py < a.H;
+    if (z == 3) {
+      if (inside) {
+        const float gd = a.gt_depth[(size_t)py * a.W + px] * a.inv_dmax;
+        const float d = a.depth[(size_t)py * a.W + px] * a.inv_dmax;
+        s_d += (gd != 0.f) ? fabsf(d - gd) : 0.f;
+      }
+      continue;
     }
-  } else {
     const float* X = a.image + z * plane;
     const float* Y = a.gt_image + z * plane;
+    __syncthreads();  // the previous item's readers of sx/sy/sh are done
     for (int i = threadIdx.x; i < kLossIn * kLossIn; i += kLossTile * kLossTile) {
       const int ly = i / kLossIn, lx = i % kLossIn;
       const int gx = x0 + lx - kHalo, gy = y0 + ly - kHalo;
@@ -129,7 +137,7 @@ mapping_loss_forward_kernel(LossArgs a, LossWindow win) {
       const float B1 = mu1_sq + mu2_sq + C1, B2 = sig1 + sig2 + C2;
       const float inv = 1.f / (B1 * B2);
       const float ssim = (A1 * A2) * inv;
-      s_ssim = ssim;
+      s_ssim += ssim;
       // partial derivatives of ssim at this pixel w.r.t. its own mu1, E[x^2], E[xy] (E[.] = windowed means)
       const float d_mu1 = (2.f * mu2 * (A2 - A1)) * inv - ssim * (2.f * mu1 * (B2 - B1)) * inv;
       const float d_exx = -ssim / B2;
@@ -141,15 +149,15 @@ mapping_loss_forward_kernel(LossArgs a, LossWindow win) {
       if (a.ssim_map) a.ssim_map[z * plane + o] = ssim;
       const float yv = sy[ty + kHalo][tx + kHalo];
       const float xr = X[o];
-      s_l1 = (yv != 0.f) ? fabsf(xr - yv) : 0.f;
+      s_l1 += (yv != 0.f) ? fabsf(xr - yv) : 0.f;
     }
   }
   // deterministic reduction: per-block partials, the last block adds them in index order
   const float b_ssim = block_sum(s_ssim, s_red);
   const float b_l1 = block_sum(s_l1, s_red);
   const float b_d = block_sum(s_d, s_red);
-  const unsigned int nblocks = gridDim.x * gridDim.y * gridDim.z;
-  const unsigned int bid = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+  const unsigned int nblocks = gridDim.x;
+  const unsigned int bid = blockIdx.x;
   __shared__ bool s_last;
   if (threadIdx.x == 0) {
     a.partial[3 * (size_t)bid + 0] = (double)b_ssim;
@@ -299,8 +307,7 @@ extern "C" {
 size_t gsicp_mapping_loss_work_bytes(int H, int W) {
   if (H <= 0 || W <= 0) return 0;
   const size_t plane = (size_t)H * W;
-  const size_t blocks = (size_t)((W + kLossTile - 1) / kLossTile) * ((H + kLossTile - 1) / kLossTile) * 4;
-  return 9 * plane * sizeof(float) + blocks * 3 * sizeof(double) + 64;
+  return 9 * plane * sizeof(float) + (size_t)kLossFwdCtas * 3 * sizeof(double) + 64;
 }
 
 static inline char* loss_partial_ptr(void* work, int H, int W) {
@@ -318,7 +325,8 @@ int gsicp_mapping_loss_forward(int H, int W, const float* d_image, const float* 
     return GSICP_EINVAL;
   }
   cudaStream_t stream = (cudaStream_t)stream_;
-  const dim3 grid((W + kLossTile - 1) / kLossTile, (H + kLossTile - 1) / kLossTile, 4);
+  const int items = ((W + kLossTile - 1) / kLossTile) * ((H + kLossTile - 1) / kLossTile) * 4;
+  const int grid = items < kLossFwdCtas ? items : kLossFwdCtas;
   LossArgs a;
   a.H = H; a.W = W; a.image = d_image; a.depth = d_depth; a.gt_image = d_gt_image; a.gt_depth = d_gt_depth;
   a.lambda_dssim = lambda_dssim; a.depth_weight = depth_weight; a.inv_dmax = 1.f / d_max;
@@ -326,7 +334,7 @@ int gsicp_mapping_loss_forward(int H, int W, const float* d_image, const float* 
   a.maps = (float*)d_work; a.ssim_map = d_ssim_map;
   char* p = loss_partial_ptr(d_work, H, W);
   a.partial = (double*)p;
-  a.counter = (unsigned int*)(p + (size_t)grid.x * grid.y * grid.z * 3 * sizeof(double));
+  a.counter = (unsigned int*)(p + (size_t)kLossFwdCtas * 3 * sizeof(double));
   a.loss = d_loss;
   a.parts = d_parts3;
   GSICP_CUDA(cudaMemsetAsync(a.counter, 0, sizeof(unsigned int), stream));  // the work buffer is caller-allocated, not zeroed
