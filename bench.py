@@ -212,7 +212,6 @@ class Ours:
             f["h_rgb"] = torch.from_numpy(f["rgb"]).pin_memory()
             f["h_depth"] = torch.from_numpy(f["depth"]).pin_memory()
             f["d_cam"] = {k: (torch.from_numpy(v).to(dev) if isinstance(v, np.ndarray) else v) for k, v in f["cam"].items()}
-        self.copy_stream = None
         self.stage_rgb = torch.empty((3, H, W), device=dev)
         self.stage_depth = torch.empty((1, H, W), device=dev)
         self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -282,16 +281,8 @@ class Ours:
         if resident:
             gt_rgb, gt_depth = f["d_rgb"], f["d_depth"]
         else:
-            # pinned host frame -> device on a copy stream, overlapped with the rasterizer forward; the loss waits for it
-            if self.copy_stream is None:
-                self.copy_stream = torch.cuda.Stream(device=self.dev)
-                self.copy_done = torch.cuda.Event()
-            cur = torch.cuda.current_stream(self.dev)
-            self.copy_stream.wait_stream(cur)  # the previous frame's loss has finished reading the staging buffers
-            with torch.cuda.stream(self.copy_stream):
-                self.stage_rgb.copy_(f["h_rgb"], non_blocking=True)
-                self.stage_depth.copy_(f["h_depth"], non_blocking=True)
-                self.copy_done.record()
+            self.stage_rgb.copy_(f["h_rgb"], non_blocking=True)
+            self.stage_depth.copy_(f["h_depth"], non_blocking=True)
             gt_rgb, gt_depth = self.stage_rgb, self.stage_depth
             st["h2d"] += f["h_rgb"].numel() * 4 + f["h_depth"].numel() * 4
         c, cam, m = f["d_cam"], self.cam, self.map
@@ -300,8 +291,6 @@ class Ours:
         depth, color, radii, is_used = self.Rasterizer(rs)(means3D=m["means3D"], means2D=self.means2D,
                                                            opacities=m["opacities"], shs=m["shs"], scales=m["scales"],
                                                            rotations=m["rotations"])
-        if not resident:
-            torch.cuda.current_stream(self.dev).wait_event(self.copy_done)
         if self.loss_kind == "ssim_fused":
             loss = self.fused.mapping_loss(color, depth, gt_rgb, gt_depth)
         elif self.loss_kind == "ssim_torch":
