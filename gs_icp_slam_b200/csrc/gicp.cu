@@ -328,6 +328,24 @@ fitness_kernel(int n, const float* __restrict__ sqd, double max_range, double* _
   }
 }
 
+// Sharded runs: every rank owns the correspondences of its source range only.  When the caller asks for them
+// (get_source_correspondence) the ranges are merged through the all-reduce callback: each entry is encoded so that it is
+// non-zero on exactly one rank (index + 1, squared distance) and zero elsewhere — the sum is exact.
+__global__ void corr_pack_kernel(int n, int begin, int end, const int32_t* __restrict__ corr, const float* __restrict__ sqd,
+                                 double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const bool mine = i >= begin && i < end;
+  out[i] = mine ? (double)(corr[i] + 1) : 0.0;
+  out[(size_t)n + i] = mine ? (double)sqd[i] : 0.0;
+}
+__global__ void corr_unpack_kernel(int n, const double* __restrict__ in, int32_t* __restrict__ corr, float* __restrict__ sqd) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  corr[i] = (int32_t)in[i] - 1;
+  sqd[i] = (float)in[(size_t)n + i];
+}
+
 // Mahalanobis + residual/Jacobian + normal-equation reduction (fgi:273-352): one THREAD per source point.
 __global__ void __launch_bounds__(kLinBlock, 1)
 linearize_kernel(PoseD T, LinArgs a) {
@@ -1258,6 +1276,20 @@ int gsicp_gicp_get_source_correspondence(gsicp_gicp* h, int32_t* corr, float* sq
   }
   if (h->src.n == 0) return GSICP_OK;
   if (!corr || !sq_dist) return GSICP_EINVAL;
+  if (h->shard_count > 1 && h->reduce) {  // merge the ranks' ranges (gathered only when asked for)
+    const int n = h->src.n;
+    int begin, end;
+    shard_range(h, n, begin, end);
+    if (int e = h->staging_dev.ensure((size_t)n * 2 * sizeof(double))) return e;
+    double* buf = h->staging_dev.as<double>();
+    GSICP_LAUNCH(corr_pack_kernel, (n + 255) / 256, 256, 0, h->stream, n, begin, end, h->corr.as<int32_t>(), h->sqd.as<float>(), buf);
+    if (h->reduce(h->reduce_user, buf, 2 * n, (void*)h->stream) != 0) {
+      set_error("all-reduce callback failed");
+      return GSICP_ECUDA;
+    }
+    GSICP_LAUNCH(corr_unpack_kernel, (n + 255) / 256, 256, 0, h->stream, n, buf, h->corr.as<int32_t>(), h->sqd.as<float>());
+    GSICP_CUDA(cudaGetLastError());
+  }
   GSICP_CUDA(cudaMemcpyAsync(corr, h->corr.ptr, (size_t)h->src.n * 4, cudaMemcpyDeviceToHost, h->stream));
   GSICP_CUDA(cudaMemcpyAsync(sq_dist, h->sqd.ptr, (size_t)h->src.n * 4, cudaMemcpyDeviceToHost, h->stream));
   GSICP_CUDA(cudaStreamSynchronize(h->stream));

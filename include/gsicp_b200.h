@@ -205,6 +205,7 @@ int gsicp_gicp_get_source_rotationsq(gsicp_gicp*, float* out);
 int gsicp_gicp_get_target_rotationsq(gsicp_gicp*, float* out);
 int gsicp_gicp_get_source_scales(gsicp_gicp*, float* out);
 int gsicp_gicp_get_target_scales(gsicp_gicp*, float* out);
+/* main.cpp:230-233.  Sharded handles merge the ranks' ranges through the all-reduce callback first (collective call). */
 int gsicp_gicp_get_source_correspondence(gsicp_gicp*, int32_t* corr, float* sq_dist);
 /* Test/diagnostic access: regularised 3x3 covariances as 9 doubles per point (row-major). */
 int gsicp_gicp_get_source_covariances(gsicp_gicp*, double* out);

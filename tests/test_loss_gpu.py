@@ -20,7 +20,7 @@ def _run(cuda, image, depth, gt, gt_depth, **kw):
     dp = depth.to(cuda).requires_grad_(True)
     loss, parts = L.mapping_loss(im, dp, gt.to(cuda), gt_depth.to(cuda), return_parts=True, **kw)
     loss.backward()
-    return float(loss), parts.cpu().numpy(), im.grad.cpu().numpy(), dp.grad.cpu().numpy()
+    return float(loss.detach()), parts.cpu().numpy(), im.grad.cpu().numpy(), dp.grad.cpu().numpy()
 
 
 @pytest.mark.parametrize("H,W,seed", [(37, 53, 1), (64, 48, 2), (480, 640, 3), (16, 16, 4), (5, 7, 5)])

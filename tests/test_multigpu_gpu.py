@@ -54,9 +54,10 @@ def align(shard):
     r = pygicp.FastGICP(); r.set_max_correspondence_distance(0.05); r.set_max_knn_distance(99999)
     if shard: r.set_shard(world, rank, sharding.make_gicp_allreduce(dev))
     r.set_input_target(tgt); r.calculate_target_covariance_with_filter(); r.set_input_source(src)
-    return r.align(np.eye(4)), r.last_iterations
-p1, i1 = align(False); pN, iN = align(True)
+    return r.align(np.eye(4)), r.last_iterations, r.get_source_correspondence()
+p1, i1, c1 = align(False); pN, iN, cN = align(True)
 assert i1 == iN and np.abs(p1 - pN).max() <= 1e-6, (i1, iN, np.abs(p1 - pN).max())
+assert np.array_equal(c1[0], cN[0]) and np.array_equal(c1[1], cN[1]), "sharded correspondences differ after the gather"
 dist.barrier(); dist.destroy_process_group()
 if rank == 0: print("MULTIGPU_OK")
 '''
