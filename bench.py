@@ -133,7 +133,7 @@ def make_sequence(n_frames, P):
 
 
 class ClockSampler:
-    """SM clock / throttle reasons during the timed region (pynvml; falls back to nvidia-smi)."""
+    """SM clock / throttle reasons sampled every 20 ms during the timed region (NVML through pynvml)."""
 
     def __init__(self, index):
         self.samples, self.reasons, self.max_mhz = [], set(), None
