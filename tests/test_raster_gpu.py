@@ -119,6 +119,61 @@ def test_options_vs_reference_cuda(cuda, active_degree, scale_modifier, size):
     ref.free()
 
 
+def test_degenerate_gaussians_vs_reference_cuda(cuda):
+    """Finite but extreme inputs: zero scales (only the 0.3 px low-pass is left), 1 km scales (the rectangle is the whole
+    screen), saturated and vanishing opacities, Gaussians exactly on the near plane and on the camera centre."""
+    from gs_icp_slam_b200 import rasterizer as R
+    from oracle import ref_cuda
+
+    if not ref_cuda.available():
+        pytest.skip("oracle/_ref/libref_cuda.so not built")
+    g, cm, t, c, cam = scene_tensors(3000, 17, cuda, size=(200, 152))
+    W, H = 200, 152
+    with torch.no_grad():
+        vis = torch.nonzero(R.mark_visible(t["means3D"], c["viewmatrix"], c["projmatrix"])).flatten()
+        a = vis[:40]
+        t["scales"][a[0:8]] = 0.0
+        t["scales"][a[8:12]] = 1000.0
+        t["scales"][a[12:16], 0] = 1000.0           # needles
+        t["opacities"][a[16:24]] = 40.0             # sigmoid -> 1 (alpha clamps at 0.99)
+        t["opacities"][a[24:32]] = -40.0            # sigmoid -> 0 (never reaches 1/255)
+        fwd = c["viewmatrix"][:3, 2]
+        t["means3D"][a[32]] = c["campos"] + 0.2 * fwd            # exactly on the near plane (z <= 0.2 culls)
+        t["means3D"][a[33]] = c["campos"] + 0.2000001 * fwd
+        t["means3D"][a[34]] = c["campos"]                        # the camera centre
+        t["rotations"][a[35]] = 0.0                              # zero quaternion (the reference does not normalise)
+    bg = torch.tensor([0.3, 0.6, 0.9], device=cuda)
+    n, depth, color, radii, is_used, geom, binning, img = _ours(t, c, H, W, bg)
+    ref = _ref(t, c, H, W, bg)
+    assert n == ref.num_rendered and torch.equal(radii, ref.radii) and torch.equal(is_used, ref.is_used)
+    pl, rg = R.export_binning(n, H, W, binning, img)
+    rpl, rrg = ref.export()
+    assert torch.equal(rg, rrg) and torch.equal(pl, rpl)
+    assert torch.equal(color.view(torch.int32), ref.color.view(torch.int32))   # bit patterns (robust to inf / nan)
+    assert torch.equal(depth.view(torch.int32), ref.depth.view(torch.int32))
+    gen = torch.Generator(device="cpu").manual_seed(3)
+    gcol = torch.randn((3, H, W), generator=gen).to(cuda)
+    gdep = torch.randn((1, H, W), generator=gen).to(cuda)
+    e = torch.Tensor([])
+    ours = R.rasterize_gaussians_backward(bg, t["means3D"], radii, e, t["scales"], t["rotations"], 1.0, e, c["viewmatrix"],
+                                          c["projmatrix"], c["tanfovx"], c["tanfovy"], gdep, gcol, t["shs"], 0, c["campos"],
+                                          geom, n, binning, img, False)
+    rgrad = ref.backward(gcol, gdep)
+    for name, o in zip(["means2D", "colors", "opacity", "means3D", "cov3D", "sh", "scales", "rotations"], ours):
+        a_, b_ = o.cpu().numpy(), rgrad[name].cpu().numpy()
+        fin = np.isfinite(b_)
+        assert np.array_equal(np.isfinite(a_), fin), name
+        d = np.where(fin, np.abs(a_.astype(np.float64) - b_), 0.0).reshape(a_.shape[0], -1).max(1)
+        scale_ = np.abs(np.where(fin, b_, 0.0)).reshape(a_.shape[0], -1).max(1)
+        # the 1 km x 2 cm "needles" produce gradients of 1e9..1e10 out of terms that cancel to 7 digits: float32 noise
+        # in both implementations (their forward output is still bit-identical); only their finiteness is compared
+        d[a[12:16].cpu().numpy()] = 0.0
+        bad = np.flatnonzero(d > 5e-4 * np.maximum(scale_, 1e-3 * scale_.max()))
+        slots = {int(v): k for k, v in enumerate(a.tolist())}
+        assert len(bad) == 0, (name, [(int(i), slots.get(int(i), -1), float(d[i]), float(scale_[i])) for i in bad[:8]])
+    ref.free()
+
+
 def test_tile_shards_partition_the_frame(cuda):
     """Tile sharding on ONE GPU: rendering the shards one after the other reproduces the unsharded frame exactly and the
     per-shard instance counts add up (the multi-GPU path without the collective)."""
