@@ -47,3 +47,24 @@ def test_loss_oracle_gradient_is_consistent():
         lm = LO.mapping_loss(image.detach() - d, depth, gt, gt_depth)[0]
         fd = float(lp - lm) / 2e-6
         assert abs(fd - float(g[c, y, x])) <= 1e-5 * max(abs(fd), 1e-4) + 1e-9
+
+
+def test_bench_reference_arm_loss_is_the_reference_formulation():
+    """bench.py's `torch_mapper_loss` (what the reference arm and the ssim_torch variant evaluate) against the golden vectors
+    of the reference's own loss code."""
+    import sys
+
+    sys.path.insert(0, os.path.dirname(HERE))
+    import bench
+
+    gold = np.load(os.path.join(HERE, "golden", "loss_ref_small.npz"))
+    for name in ("a", "b"):
+        H, W, seed = (int(v) for v in gold[f"{name}_shape"])
+        image, depth, gt, gt_depth = inputs(H, W, seed)
+        image.requires_grad_(True)
+        depth.requires_grad_(True)
+        loss = bench.torch_mapper_loss(image, depth, gt, gt_depth)
+        loss.backward()
+        assert abs(float(loss.detach()) - float(gold[f"{name}_loss"])) <= 1e-6
+        assert np.abs(image.grad.numpy() - gold[f"{name}_grad_image"]).max() <= 1e-5 * np.abs(gold[f"{name}_grad_image"]).max()
+        assert np.abs(depth.grad.numpy() - gold[f"{name}_grad_depth"]).max() <= 1e-6 * np.abs(gold[f"{name}_grad_depth"]).max() + 1e-12
