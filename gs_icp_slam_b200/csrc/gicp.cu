@@ -285,10 +285,12 @@ correspond_kernel(GridView tgt, PoseD T, int begin, int end, double max_corr_sq,
   const int i = begin + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
   if (i >= end) return;  // warp-uniform
   const float px = src_xyz[3 * (size_t)i], py = src_xyz[3 * (size_t)i + 1], pz = src_xyz[3 * (size_t)i + 2];
-  // ((r0*x + r1*y) + r2*z) + t in fp32 without contraction (fgi:260-262)
-  const float tx = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(T.Rf[0][0], px), __fmul_rn(T.Rf[0][1], py)), __fmul_rn(T.Rf[0][2], pz)), T.tf[0]);
-  const float ty = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(T.Rf[1][0], px), __fmul_rn(T.Rf[1][1], py)), __fmul_rn(T.Rf[1][2], pz)), T.tf[1]);
-  const float tz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(T.Rf[2][0], px), __fmul_rn(T.Rf[2][1], py)), __fmul_rn(T.Rf[2][2], pz)), T.tf[2]);
+  // fp32 transform without contraction, in the order Eigen's packet product evaluates trans_f * getVector4fMap()
+  // (fgi:260): (c0*x + c1*y) + (c2*z + c3*1).  Pinned against the reference build (tests/test_gicp_reference.py): the
+  // squared distances below are bit-identical to fast_gicp's.
+  const float tx = __fadd_rn(__fadd_rn(__fmul_rn(T.Rf[0][0], px), __fmul_rn(T.Rf[0][1], py)), __fadd_rn(__fmul_rn(T.Rf[0][2], pz), T.tf[0]));
+  const float ty = __fadd_rn(__fadd_rn(__fmul_rn(T.Rf[1][0], px), __fmul_rn(T.Rf[1][1], py)), __fadd_rn(__fmul_rn(T.Rf[1][2], pz), T.tf[1]));
+  const float tz = __fadd_rn(__fadd_rn(__fmul_rn(T.Rf[2][0], px), __fmul_rn(T.Rf[2][1], py)), __fadd_rn(__fmul_rn(T.Rf[2][2], pz), T.tf[2]));
   float d2;
   uint32_t id;
   grid_nn_warp(tgt, tx, ty, tz, d2, id);

@@ -581,7 +581,9 @@ struct Oracle {
           const float* p = sx + 3 * (size_t)i;
           if (update_corr) {
             float pt[3];
-            for (int d = 0; d < 3; d++) pt[d] = ((Rf[d][0] * p[0] + Rf[d][1] * p[1]) + Rf[d][2] * p[2]) + tf[d];
+            // Eigen evaluates the packet product trans_f * getVector4fMap() (fgi:260) as (c0*x + c1*y) + (c2*z + c3*1):
+            // pinned against the reference build (oracle/_ref/fast_gicp, tests/test_gicp_reference.py)
+            for (int d = 0; d < 3; d++) pt[d] = (Rf[d][0] * p[0] + Rf[d][1] * p[1]) + (Rf[d][2] * p[2] + tf[d]);
             tgt.tree.search(pt, 1, nn);
             const float d2 = nn.empty() ? FLT_MAX : nn[0].d2;
             sqd[i] = d2;
@@ -807,7 +809,7 @@ double go_get_fitness_score(void* h, double max_range) {
   for (int i = 0; i < o->src.n; i++) {
     const float* p = &o->src.xyz[3 * (size_t)i];
     float q[3];
-    for (int r = 0; r < 3; r++) q[r] = ((T[4 * r] * p[0] + T[4 * r + 1] * p[1]) + T[4 * r + 2] * p[2]) + T[4 * r + 3];
+    for (int r = 0; r < 3; r++) q[r] = (T[4 * r] * p[0] + T[4 * r + 1] * p[1]) + (T[4 * r + 2] * p[2] + T[4 * r + 3]);  // pcl::transformPointCloud order
     o->tgt.tree.search(q, 1, nn);
     if (!nn.empty() && (double)nn[0].d2 <= max_range) {
       sum += (double)nn[0].d2;

@@ -146,6 +146,11 @@ class FastGICP:
     def has_converged(self):
         return bool(self._L.go_has_converged(self._h))
 
+    def get_final_hessian(self):  # LsqRegistration binding, main.cpp:170
+        H = np.empty((6, 6), dtype=np.float64)
+        self._L.go_get_final_hessian(self._h, H.ctypes.data)
+        return H
+
     def _vec(self, size, get, dtype=np.float32, shape=None):
         n = getattr(self._L, size)(self._h)
         out = np.empty(n if shape is None else (n,) + shape, dtype=dtype)

@@ -3,6 +3,10 @@ import sys
 
 import pytest
 
+# OpenMP teams of the CPU oracles / the reference build: libgomp's default busy-wait burns the (few) cores of the build
+# container between parallel regions; must be set before libgomp is loaded
+os.environ.setdefault("OMP_WAIT_POLICY", "passive")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
