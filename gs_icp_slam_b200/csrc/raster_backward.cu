@@ -3,12 +3,18 @@
 // Replaces CudaRasterizer::Rasterizer::backward (DGR/cuda_rasterizer/rasterizer_impl.cu:351-454):
 //   BACKWARD::render (backward.cu:429-657)  +  computeCov2DCUDA (:144-294)  +  preprocessCUDA (:369-426)
 //
-// render backward: the reference issues up to 12 global float atomicAdd per contributing
-// pixel-Gaussian pair.  Here each warp owns an 8x4 sub-tile, culls the staged batch exactly as the
-// forward does, reduces the 12 partial gradients of a surviving instance across its 32 lanes with
-// shuffles, adds them to a per-CTA shared-memory accumulator, and the CTA flushes ONE set of 12
-// global atomics per (tile, instance) at the end of each batch: global atomics drop from
-// 12 * pairs to 12 * R.
+// render backward: the reference issues up to 12 global float atomicAdd per contributing pixel-Gaussian pair.  Here each
+// warp owns an 8x4 sub-tile, culls the staged batch exactly as the forward does, replays the blend back to front, and per
+// surviving (sub-tile, instance) only TWO per-pixel scalars are formed: t = G * dL/dalpha and w = alpha * T.  The
+// reference's 12 per-pair gradient expressions (backward.cu:575-654) are linear in twelve MOMENTS of those two fields over
+// the pixels (t against {1, dx, dy, dx^2, dx dy, dy^2}; w against dL/dpix_depth {1, dx, dy} and dL/dpix_{r,g,b}), and a sum
+// over the 32 pixels of a warp against fixed per-pixel weights is a small matrix product: the (t, w) values of 8 survivors
+// are transposed through 2.3 KB of shared memory per warp and reduced by the tensor cores
+// (mma.sync.m16n8k8 tf32, fp32 accumulate; values split hi/lo so the products carry 22 mantissa bits):
+//     D[12 moments x 8 instances] = A[12 x 32 pixels] * B[32 pixels x 8 instances]
+// with the pixel-offset basis taken in the warp's own integer frame (exact in tf32) and shifted to the Gaussian's centre
+// afterwards.  20 MMAs + 4 REDs serve 8 instances, instead of 13 shuffles + 26 selects + 13 adds + 1 RED per instance.
+// Global atomics: 12 per (sub-tile, instance) that blended anything, vs 12 per (pixel, Gaussian) pair in the reference.
 //
 // per-Gaussian backward: computeCov2D backward and the preprocess backward are one kernel (the
 // intermediate dL_dcov3D / dL_dmeans never round-trip through HBM between two launches).
@@ -19,24 +25,39 @@
 
 namespace gsicp {
 
-constexpr int kG = 12;  // gradient floats per instance: rgb(3) depth(1) mean2D(2) conic(3) cov_zx cov_yz opacity
+constexpr int kG = 12;    // moments per Gaussian (see below)
+constexpr int kGrp = 8;   // survivors reduced per MMA group (the N dimension of m16n8k8)
+constexpr int kRow = 36;  // words per staged row: 32 pixels + 4 pad (conflict-free 128-bit fragment loads)
+constexpr int kWarps = kTilePixels / 32;
 
-__device__ __forceinline__ float warp_sum(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
+// Dynamic shared memory of render_backward_kernel (59 392 B; three CTAs per SM):
+struct __align__(16) BwdSmem {
+  float4 a[2][kTilePixels], b[2][kTilePixels], c[2][kTilePixels];  // double-buffered staging of 256 splat records
+  float tq[kWarps][kGrp * kRow], wq[kWarps][kGrp * kRow];          // per-warp transposition buffers of the MMA reduction
+  float4 aw[kWarps][4][32];                                        // per-warp constant A fragments of the w-block
+};
+
+// D += A * B, A 16x8 (row major), B 8x8 (column major), tf32 inputs (the low 13 mantissa bits are ignored), fp32 accumulate.
+// Fragment layout (PTX ISA, mma.m16n8k8 .tf32), g = lane >> 2, t = lane & 3:
+//   a0 = A[g][t], a1 = A[g+8][t], a2 = A[g][t+4], a3 = A[g+8][t+4];  b0 = B[t][g], b1 = B[t+4][g];
+//   d0 = D[g][2t], d1 = D[g][2t+1], d2 = D[g+8][2t], d3 = D[g+8][2t+1].
+__device__ __forceinline__ void mma_tf32(float (&d)[4], float a0, float a1, float a2, float a3, float b0, float b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(__float_as_uint(a0)), "r"(__float_as_uint(a1)), "r"(__float_as_uint(a2)), "r"(__float_as_uint(a3)),
+        "r"(__float_as_uint(b0)), "r"(__float_as_uint(b1)));
 }
+// x = hi + lo with hi exactly representable in tf32 (lo keeps the next 11 bits once the MMA drops its own low bits)
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
 
-// moments[P][12]: per Gaussian, summed over every pixel it was blended into (one fp32 RED per lane-owned sum):
-//   [0..2] sum w dL/dpix_rgb        (= dL/dcolour)             w = alpha * T
-//   [3]    sum v                    (= dL/ddepth)              v = w * dL/dpix_depth
-//   [4]    sum t                    (= dL/dopacity)            t = G (dL/dalpha + dL/dalpha_d)
-//   [5..9] sum u dx, u dy, u dx^2, u dx dy, u dy^2             u = opacity * t
-//   [10,11] sum v dx, v dy
-// The reference's 12 per-pair gradient expressions (backward.cu:575-654) are linear in these moments with
-// per-Gaussian coefficients; gaussian_backward_kernel forms them once per Gaussian.
+// moments[P][12], summed over every pixel the Gaussian was blended into (dx = mean2D.x - pixel.x, dy likewise):
+//   [0..5]  sum t {1, dx, dy, dx^2, dx dy, dy^2}     t = G (dL/dalpha + dL/dalpha_d)     ([0] = dL/dopacity)
+//   [6..8]  sum v {1, dx, dy}                         v = w dL/dpix_depth, w = alpha T   ([6] = dL/ddepth)
+//   [9..11] sum w dL/dpix_{r,g,b}                                                         (= dL/dcolour)
+// gaussian_backward_kernel forms the reference's gradients from them with per-Gaussian coefficients.
 template <bool kCull>
-__global__ void __launch_bounds__(kTilePixels, 4)
+__global__ void __launch_bounds__(kTilePixels, 3)
 render_backward_kernel(const uint32_t* __restrict__ tile_order, const uint2* __restrict__ ranges,
                        const uint32_t* __restrict__ point_list, int W, int H,
                        int tiles_x, const float* __restrict__ bg, const Splat* __restrict__ splats,
@@ -51,11 +72,11 @@ render_backward_kernel(const uint32_t* __restrict__ tile_order, const uint2* __r
   const int px = wx0 + (lane & 7), py = wy0 + (lane >> 3);
   const bool inside = px < W && py < H;
   const float pxf = (float)px, pyf = (float)py;
+  const float wx0f = (float)wx0, wy0f = (float)wy0;
   const int pix = py * W + px;
 
-  // double-buffered staging of 256 instances: one barrier per batch, loads of batch k+1 overlap the math of batch k
-  __shared__ float4 sA[2][kTilePixels], sB[2][kTilePixels], sC[2][kTilePixels];
-  __shared__ uint32_t sId[2][kTilePixels];
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  BwdSmem& sm = *reinterpret_cast<BwdSmem*>(smem_raw);
 
   const uint2 range = ranges[tile];
   const int total = (int)(range.y - range.x);
@@ -80,42 +101,136 @@ render_backward_kernel(const uint32_t* __restrict__ tile_order, const uint2* __r
   const float bg_dot_ddepth = 15.f * dpd;
   const float bg_term = T_final * (bg_dot_dpixel + bg_dot_ddepth);  // background share of dL/dalpha + dL/dalpha_d
 
+  // ---- A operand of the reduction: rows = moments, columns = the warp's 32 pixels (k = lane; i = k & 7, j = k >> 3) ----
+  // Thread (g8, t4) supplies, for k-step ks, the columns k = 8 ks + t4 and k + 4 (i = t4 / t4 + 4, j = ks) of its rows.
+  //   t-block (B = t values):  row g8 < 6 = {1, i, j, i^2, i j, j^2} in the warp's integer frame — exact in tf32, and a
+  //     polynomial in j = ks: at = alpha + j (beta + gamma j) with per-thread constants (5 registers).
+  //   w-block (B = w values):  row g8 < 6 = HIGH tf32 part of {dpd, dpd i, dpd j, dpr, dpg, dpb}(pixel k), row 8 + g8 = the
+  //     LOW part (dp* = dL/dpix_*): both parts ride the same MMA and are added in the epilogue.  Kept in shared memory.
+  const int g8 = lane >> 2, t4 = lane & 3;
+  const float fi0 = (float)t4, fi1 = (float)(t4 + 4);
+  const float t_al0 = g8 == 0 ? 1.f : g8 == 1 ? fi0 : g8 == 3 ? fi0 * fi0 : 0.f;
+  const float t_al1 = g8 == 0 ? 1.f : g8 == 1 ? fi1 : g8 == 3 ? fi1 * fi1 : 0.f;
+  const float t_be0 = g8 == 2 ? 1.f : g8 == 4 ? fi0 : 0.f;
+  const float t_be1 = g8 == 2 ? 1.f : g8 == 4 ? fi1 : 0.f;
+  const float t_ga = g8 == 5 ? 1.f : 0.f;
+#pragma unroll
+  for (int ks = 0; ks < 4; ks++) {
+    float hi[2], lo[2];
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const int k = 8 * ks + t4 + 4 * h;
+      const float fi = (float)(k & 7), fj = (float)(k >> 3);
+      const float kr = __shfl_sync(0xffffffffu, dpr, k), kg = __shfl_sync(0xffffffffu, dpg, k);
+      const float kb = __shfl_sync(0xffffffffu, dpb, k), kd = __shfl_sync(0xffffffffu, dpd, k);
+      const float v = g8 == 0 ? kd : g8 == 1 ? kd * fi : g8 == 2 ? kd * fj : g8 == 3 ? kr : g8 == 4 ? kg : g8 == 5 ? kb : 0.f;
+      hi[h] = tf32_hi(v);
+      lo[h] = v - hi[h];
+    }
+    sm.aw[warp][ks][lane] = make_float4(hi[0], lo[0], hi[1], lo[1]);  // {a0, a1, a2, a3} of k-step ks
+  }
+  float* const myT = sm.tq[warp];
+  float* const myW = sm.wq[warp];
+  const int wpos = (lane & 3) * 8 + (lane >> 2);  // pixel k = lane sits at word (k & 3) * 8 + (k >> 2): the 8 pixels a
+                                                  // thread needs for its B fragments are 8 consecutive words
+  int cnt = 0;                                    // survivors staged in the current group (warp-uniform)
+  float m_cx = 0.f, m_cy = 0.f;                   // lane s: centre of survivor s in the warp's frame, and its Gaussian
+  uint32_t m_id = 0;
+
+  // Reduce the staged group: D = A * B on the tensor cores, shift the pixel-frame moments to each Gaussian's centre,
+  // one fp32 RED per moment.
+  auto flush = [&]() {
+    for (int s2 = cnt; s2 < kGrp; s2++) {  // unused slots contribute zero
+      myT[s2 * kRow + wpos] = 0.f;
+      myW[s2 * kRow + wpos] = 0.f;
+    }
+    __syncwarp();
+    const float4* rt = reinterpret_cast<const float4*>(myT + g8 * kRow + t4 * 8);
+    const float4* rw = reinterpret_cast<const float4*>(myW + g8 * kRow + t4 * 8);
+    float dT[4] = {0.f, 0.f, 0.f, 0.f}, dW[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int half = 0; half < 2; half++) {  // words 4 half .. 4 half + 3 of the row feed the k-steps 2 half and 2 half + 1
+      const float4 tv = rt[half], wv = rw[half];
+      const float bt[4] = {tv.x, tv.y, tv.z, tv.w}, bw[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+      for (int q = 0; q < 2; q++) {
+        const int ks = 2 * half + q;
+        const float fj = (float)ks;
+        const float at0 = t_al0 + fj * (t_be0 + t_ga * fj), at1 = t_al1 + fj * (t_be1 + t_ga * fj);
+        const float th0 = tf32_hi(bt[2 * q]), th1 = tf32_hi(bt[2 * q + 1]);
+        mma_tf32(dT, at0, at0, at1, at1, th0, th1);                                // rows 8..15 of dT are not used
+        mma_tf32(dT, at0, at0, at1, at1, bt[2 * q] - th0, bt[2 * q + 1] - th1);
+        const float4 aw = sm.aw[warp][ks][lane];
+        const float wh0 = tf32_hi(bw[2 * q]), wh1 = tf32_hi(bw[2 * q + 1]);
+        mma_tf32(dW, aw.x, aw.y, aw.z, aw.w, wh0, wh1);
+        mma_tf32(dW, aw.x, aw.y, aw.z, aw.w, bw[2 * q] - wh0, bw[2 * q + 1] - wh1);
+      }
+    }
+    __syncwarp();  // every lane has read its fragments: the slots may be overwritten
+    // thread (g8, t4) holds moment row g8 of the instances 2 t4 (index 0) and 2 t4 + 1 (index 1):
+    // t-block dT[h]; w-block high + low part dW[h] + dW[2 + h]
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const int n = 2 * t4 + h;
+      const float own_t = dT[h], own_w = dW[h] + dW[2 + h];
+      // pixel-frame sums of rows 0, 1, 2 of this instance live in the threads (0, t4), (1, t4), (2, t4)
+      const float S0 = __shfl_sync(0xffffffffu, own_t, t4), S1 = __shfl_sync(0xffffffffu, own_t, 4 + t4);
+      const float S2 = __shfl_sync(0xffffffffu, own_t, 8 + t4);
+      const float V0 = __shfl_sync(0xffffffffu, own_w, t4);
+      const float cx = __shfl_sync(0xffffffffu, m_cx, n), cy = __shfl_sync(0xffffffffu, m_cy, n);
+      const uint32_t gid = __shfl_sync(0xffffffffu, m_id, n);
+      // dx = cx - i, dy = cy - j: sum f dx = cx S0 - S_i, sum f dx^2 = cx^2 S0 - 2 cx S_i + S_ii, ...
+      float gt, gw = own_w;
+      if (g8 == 0)      { gt = own_t; }
+      else if (g8 == 1) { gt = cx * S0 - own_t;                            gw = cx * V0 - own_w; }
+      else if (g8 == 2) { gt = cy * S0 - own_t;                            gw = cy * V0 - own_w; }
+      else if (g8 == 3) { gt = own_t + cx * (cx * S0 - 2.f * S1); }
+      else if (g8 == 4) { gt = own_t + (cx * cy * S0 - cx * S2 - cy * S1); }
+      else              { gt = own_t + cy * (cy * S0 - 2.f * S2); }
+      if (g8 < 6 && n < cnt) {
+        float* dst = moments + (size_t)gid * kG;
+        atomicAdd(dst + g8, gt);
+        atomicAdd(dst + 6 + g8, gw);
+      }
+    }
+    cnt = 0;
+  };
+
   float last_alpha = 0.f, last_r = 0.f, last_g = 0.f, last_b = 0.f, last_depth = 0.f;
   float acc_r = 0.f, acc_g = 0.f, acc_b = 0.f, acc_d = 0.f;
-  // lane roles of the recursive-halving reduction (see below)
-  const bool b16 = lane & 16, b8 = lane & 8, b4 = lane & 4, b2 = lane & 2;
-  const int red_var = (b16 ? 6 : 0) + (b8 ? 3 : 0) + (b4 ? 2 : (b2 ? 1 : 0));
-  const bool red_valid = !(b4 && b2) && !(lane & 1);
 
   // Back to front: batch `base` covers list positions [total-base-n, total-base), staged reversed
   // (slot k = position total-base-1-k) like backward.cu:519-531.
   auto stage = [&](int base, int buf) {
     const int n = min(kTilePixels, total - base);
     if (tid < n) {
-      const uint32_t g = point_list[range.y - 1 - base - tid];
-      const Splat* sp = splats + g;
-      sId[buf][tid] = g;
-      sA[buf][tid] = __ldg(&sp->a);
-      sB[buf][tid] = __ldg(&sp->b);
-      sC[buf][tid] = __ldg(&sp->c);
+      const Splat* sp = splats + point_list[range.y - 1 - base - tid];
+      cp_async16(&sm.a[buf][tid], &sp->a);
+      cp_async16(&sm.b[buf][tid], &sp->b);
+      cp_async16(&sm.c[buf][tid], &sp->c);
     }
+    cp_async_commit();
   };
   if (total > 0) stage(0, 0);
 
   for (int base = 0, buf = 0; base < total; base += kTilePixels, buf ^= 1) {
     const int n = min(kTilePixels, total - base);
+    cp_async_wait_all();
     __syncthreads();  // batch `base` is staged; every warp has finished reading the other buffer
     if (base + kTilePixels < total) stage(base + kTilePixels, buf ^ 1);
 
     const int first_pos = total - base;  // 1-based contributor id of slot 0
     if (first_pos - (n - 1) > warp_last) continue;  // the whole batch lies behind this warp's last contributor
+    const float4* sA = sm.a[buf];
+    const float4* sB = sm.b[buf];
+    const float4* sC = sm.c[buf];
     for (int c0 = 0; c0 < n; c0 += 32) {
       if (first_pos - c0 - 31 > warp_last && c0 + 32 <= n) continue;  // whole chunk behind the last contributor
       uint32_t mask;
       {
         const int j = c0 + lane;
         bool hit = (j < n) && (first_pos - j <= warp_last);
-        if (kCull) hit = hit && subtile_hit(sA[buf][j < n ? j : 0], sB[buf][j < n ? j : 0], (float)wx0, (float)wy0, 7.f, 3.f);
+        if (kCull) hit = hit && subtile_hit(sA[j < n ? j : 0], sB[j < n ? j : 0], wx0f, wy0f, 7.f, 3.f);
         mask = __ballot_sync(0xffffffffu, hit);
       }
       while (mask) {
@@ -123,24 +238,21 @@ render_backward_kernel(const uint32_t* __restrict__ tile_order, const uint2* __r
         mask &= mask - 1;
         const int j = c0 + bit;
         const int contributor = first_pos - j;  // 1-based; reference compares (contributor-1) >= last (backward.cu:540-542)
-        const float4 a = sA[buf][j], b = sB[buf][j];
+        const float4 a = sA[j], b = sB[j];
         const float dx = a.x - pxf, dy = a.y - pyf;
         const float power = -0.5f * (a.z * dx * dx + b.x * dy * dy) - a.w * dx * dy;
         const float G = expf(power);
         const float alpha = fminf(0.99f, b.y * G);
         const bool active = inside && (contributor <= last_contributor) && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
 
-        const unsigned act = __ballot_sync(0xffffffffu, active);
-        if (!act) continue;  // no pixel of this sub-tile blended the instance: skip the gradient arithmetic
+        if (!__any_sync(0xffffffffu, active)) continue;  // no pixel of this sub-tile blended the instance
 
-        float g[kG];
-#pragma unroll
-        for (int k = 0; k < kG; k++) g[k] = 0.f;
+        float tq = 0.f, wq = 0.f;
         if (active) {
-          const float4 c = sC[buf][j];
+          const float4 c = sC[j];
           const float inv = __frcp_rn(1.f - alpha);  // correctly rounded reciprocal, shared by the three divisions
           T = T * inv;                               // transmittance in front of this Gaussian (backward.cu:555)
-          const float w = alpha * T;                 // d(pixel channel)/d(colour), also d(pixel depth)/d(depth)
+          wq = alpha * T;                            // d(pixel channel)/d(colour), also d(pixel depth)/d(depth)
 
           // colour and depth blended behind this Gaussian (backward.cu:563-576, 617-620)
           acc_r = last_alpha * last_r + (1.f - last_alpha) * acc_r;
@@ -154,54 +266,20 @@ render_backward_kernel(const uint32_t* __restrict__ tile_order, const uint2* __r
           // dL/dalpha (colour) + dL/dalpha_d (depth; same alpha and transmittance, T_d == T bit for bit)
           const float dsum = ((c.x - acc_r) * dpr + (c.y - acc_g) * dpg + (c.z - acc_b) * dpb + (depth - acc_d) * dpd) * T -
                              bg_term * inv;
-          const float t = G * dsum;
-          const float u = b.y * t;
-          const float v = w * dpd;
-          const float udx = u * dx, udy = u * dy;
-          g[0] = w * dpr; g[1] = w * dpg; g[2] = w * dpb;
-          g[3] = v;
-          g[4] = t;
-          g[5] = udx;
-          g[6] = udy;
-          g[7] = udx * dx;
-          g[8] = udx * dy;
-          g[9] = udy * dy;
-          g[10] = v * dx;
-          g[11] = v * dy;
+          tq = G * dsum;
         }
-        float* dst = moments + (size_t)sId[buf][j] * kG;
-        if (__popc(act) <= 2) {
-          // one or two pixels of the sub-tile see this Gaussian (ellipse edge): add them directly
-          if (active) {
-#pragma unroll
-            for (int k = 0; k < kG; k++) atomicAdd(dst + k, g[k]);
-          }
-        } else {
-          // Recursive-halving reduction: at each step a lane keeps half of its running sums and hands the other half to
-          // its partner, so the 12 sums over 32 lanes cost 6+3+2+1+1 = 13 shuffles (a butterfly per value: 60).
-          // Sum k ends up in the lane with red_var == k, which issues ONE fp32 RED to moments[gaussian][k]:
-          // 12 consecutive addresses per instance, fire-and-forget — no shared-memory accumulator (whose float add is
-          // a CAS loop on this architecture), no flush, no extra barrier.
-          float h[6], q[3];
-#pragma unroll
-          for (int i = 0; i < 6; i++) {
-            const float send = b16 ? g[i] : g[i + 6], keep = b16 ? g[i + 6] : g[i];
-            h[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-          }
-#pragma unroll
-          for (int i = 0; i < 3; i++) {
-            const float send = b8 ? h[i] : h[i + 3], keep = b8 ? h[i + 3] : h[i];
-            q[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-          }
-          const float r0 = (b4 ? q[2] : q[0]) + __shfl_xor_sync(0xffffffffu, b4 ? q[0] : q[2], 4);
-          const float r1 = (b4 ? 0.f : q[1]) + __shfl_xor_sync(0xffffffffu, b4 ? q[1] : 0.f, 4);
-          float sum = (b2 ? r1 : r0) + __shfl_xor_sync(0xffffffffu, b2 ? r0 : r1, 2);
-          sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-          if (red_valid) atomicAdd(dst + red_var, sum);
+        myT[cnt * kRow + wpos] = tq;
+        myW[cnt * kRow + wpos] = wq;
+        if (lane == cnt) {
+          m_cx = a.x - wx0f;
+          m_cy = a.y - wy0f;
+          m_id = point_list[range.y - 1 - base - j];
         }
+        if (++cnt == kGrp) flush();
       }
     }
   }
+  if (cnt > 0) flush();
 }
 
 // ------------------------------------------------------------------------------------------
@@ -277,19 +355,43 @@ __device__ __forceinline__ F3 sh_backward(int idx, const BwdArgs& a, uint8_t cla
       }
     }
   }
+  // coefficients above the active degree get no gradient (the caller's buffer is uninitialised: write the zeros)
+  for (int c = (a.D + 1) * (a.D + 1); c < a.M; c++) dL_dsh[c] = {0.f, 0.f, 0.f};
   const F3 dL_ddir = {dot3(dRGBdx, dL_dRGB), dot3(dRGBdy, dL_dRGB), dot3(dRGBdz, dL_dRGB)};
   return dnormv(dir_orig, dL_ddir);
 }
 
 __global__ void __launch_bounds__(256)
 gaussian_backward_kernel(BwdArgs a, const int32_t* __restrict__ radii, const uint8_t* __restrict__ clamped,
-                         const float* __restrict__ moments, const Splat* __restrict__ splats, int W, int H,
+                         float* __restrict__ moments, const Splat* __restrict__ splats, int W, int H,
                          float* __restrict__ dL_dmean2D, float* __restrict__ dL_dcolors,
                          float* __restrict__ dL_dopacity, float* __restrict__ dL_dmeans3D,
                          float* __restrict__ dL_dcov3D, float* __restrict__ dL_dsh, float* __restrict__ dL_dscales,
                          float* __restrict__ dL_drots) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= a.P || !(radii[idx] > 0)) return;
+  if (idx >= a.P) return;
+  // dL_dmean2D is [P][3]; the third component is never written by the reference either (stays zero)
+  dL_dmean2D[3 * (size_t)idx + 2] = 0.f;
+  if (!(radii[idx] > 0)) {
+    // Invisible Gaussian: every gradient row is exactly zero.  The kernel writes the zeros itself, so the caller hands
+    // over uninitialised memory: no P-sized fill launch precedes the backward (the reference zero-fills ten tensors,
+    // rasterize_points.cu:158-167).
+    dL_dmean2D[3 * (size_t)idx + 0] = 0.f;
+    dL_dmean2D[3 * (size_t)idx + 1] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      dL_dcolors[3 * (size_t)idx + i] = 0.f;
+      dL_dmeans3D[3 * (size_t)idx + i] = 0.f;
+      dL_dscales[3 * (size_t)idx + i] = 0.f;
+    }
+    dL_dopacity[idx] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 6; i++) dL_dcov3D[6 * (size_t)idx + i] = 0.f;
+    reinterpret_cast<float4*>(dL_drots)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (dL_dsh)
+      for (int i = 0; i < 3 * a.M; i++) dL_dsh[(size_t)idx * 3 * a.M + i] = 0.f;
+    return;
+  }
 
   const float3 mean = make_float3(a.means[3 * idx], a.means[3 * idx + 1], a.means[3 * idx + 2]);
   float cov3[6];
@@ -299,20 +401,22 @@ gaussian_backward_kernel(BwdArgs a, const int32_t* __restrict__ radii, const uin
 #pragma unroll
     for (int i = 0; i < 6; i++) cov3[i] = a.cov_pre[6 * (size_t)idx + i];
   } else {
-    scale = make_float3(a.scales[3 * idx], a.scales[3 * idx + 1], a.scales[3 * idx + 2]);
-    q = reinterpret_cast<const float4*>(a.rots)[idx];
+    if (a.scales) scale = make_float3(a.scales[3 * idx], a.scales[3 * idx + 1], a.scales[3 * idx + 2]);
+    if (a.rots) q = reinterpret_cast<const float4*>(a.rots)[idx];
     cov3d_from_scale_rot(scale, a.scale_modifier, q, cov3);
   }
   // ---- render gradients from the moments (reference expressions: backward.cu:604-654) ----
-  const float4 m0 = reinterpret_cast<const float4*>(moments)[3 * (size_t)idx];
-  const float4 m1 = reinterpret_cast<const float4*>(moments)[3 * (size_t)idx + 1];
-  const float4 m2 = reinterpret_cast<const float4*>(moments)[3 * (size_t)idx + 2];
-  const float v0 = m0.w, tt = m1.x, ux = m1.y, uy = m1.z, uxx = m1.w, uxy = m2.x, uyy = m2.y, vx = m2.z, vy = m2.w;
+  float4* mrow = reinterpret_cast<float4*>(moments) + 3 * (size_t)idx;
+  const float4 m0 = mrow[0], m1 = mrow[1], m2 = mrow[2];
+  mrow[0] = mrow[1] = mrow[2] = make_float4(0.f, 0.f, 0.f, 0.f);  // consumed: a second backward on the same state starts from zero
   const Splat sp = splats[idx];
-  const float cA = sp.a.z, cB = sp.a.w, cC = sp.b.x, czx = sp.b.z, cyz = sp.b.w;
-  dL_dcolors[3 * (size_t)idx + 0] = m0.x;
-  dL_dcolors[3 * (size_t)idx + 1] = m0.y;
-  dL_dcolors[3 * (size_t)idx + 2] = m0.z;
+  const float cA = sp.a.z, cB = sp.a.w, cC = sp.b.x, opac = sp.b.y, czx = sp.b.z, cyz = sp.b.w;
+  // u = opacity * t (backward.cu:606-612 multiply by con_o.w per pair; here once per Gaussian)
+  const float tt = m0.x, ux = opac * m0.y, uy = opac * m0.z, uxx = opac * m0.w, uxy = opac * m1.x, uyy = opac * m1.y;
+  const float v0 = m1.z, vx = m1.w, vy = m2.x;
+  dL_dcolors[3 * (size_t)idx + 0] = m2.y;
+  dL_dcolors[3 * (size_t)idx + 1] = m2.z;
+  dL_dcolors[3 * (size_t)idx + 2] = m2.w;
   dL_dopacity[idx] = tt;
   const float g2x = (-cA * ux - cB * uy - (czx * cA + cyz * cB) * v0) * (0.5f * W);
   const float g2y = (-cC * uy - cB * ux - (czx * cB + cyz * cC) * v0) * (0.5f * H);
@@ -414,7 +518,7 @@ gaussian_backward_kernel(BwdArgs a, const int32_t* __restrict__ radii, const uin
 
   // ---- SH path ----
   if (a.shs) {
-    const F3 dRGB = {m0.x, m0.y, m0.z};
+    const F3 dRGB = {m2.y, m2.z, m2.w};
     const F3 dm = sh_backward(idx, a, clamped[idx], dRGB, dL_dsh);
     dmean = dmean + dm;
   }
@@ -423,7 +527,10 @@ gaussian_backward_kernel(BwdArgs a, const int32_t* __restrict__ radii, const uin
   dL_dmeans3D[3 * (size_t)idx + 2] = dmean.z;
 
   // ---- scale / rotation (backward.cu:298-364; no quaternion-normalisation backward) ----
-  if (a.scales) {
+  if (!a.scales) {  // precomputed 3D covariance: no scale / rotation gradient (rows stay zero like the reference's)
+    dL_dscales[3 * (size_t)idx + 0] = dL_dscales[3 * (size_t)idx + 1] = dL_dscales[3 * (size_t)idx + 2] = 0.f;
+    reinterpret_cast<float4*>(dL_drots)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+  } else {
     const M3 R = quat_to_m3(q.x, q.y, q.z, q.w);
     const float3 s = make_float3(a.scale_modifier * scale.x, a.scale_modifier * scale.y, a.scale_modifier * scale.z);
     M3 S;
@@ -565,6 +672,20 @@ static int allreduce_visible_moments(int P, const int32_t* d_radii, float* momen
 
 using namespace gsicp;
 
+// render_backward_kernel needs more than the 48 KB of shared memory a kernel gets by default: opt in once per device.
+static int ensure_bwd_smem_attr() {
+  static std::mutex mu;
+  static bool done[64] = {};
+  int dev = 0;
+  GSICP_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(mu);
+  if (dev < 0 || dev >= 64 || done[dev]) return GSICP_OK;
+  GSICP_CUDA(cudaFuncSetAttribute(render_backward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BwdSmem)));
+  GSICP_CUDA(cudaFuncSetAttribute(render_backward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BwdSmem)));
+  done[dev] = true;
+  return GSICP_OK;
+}
+
 extern "C" int gsicp_raster_set_allreduce(gsicp_allreduce_f32_fn fn, void* user) {
   std::lock_guard<std::mutex> lock(g_bwd.mu);
   g_bwd.fn = fn;
@@ -572,7 +693,9 @@ extern "C" int gsicp_raster_set_allreduce(gsicp_allreduce_f32_fn fn, void* user)
   return GSICP_OK;
 }
 
-extern "C" size_t gsicp_raster_backward_work_bytes(int P) { return (size_t)(P > 0 ? P : 0) * kG * sizeof(float) + 16; }
+// The render moments live in the geometry buffer the forward pass allocated (GeomState::moments, zeroed for the visible
+// Gaussians by preprocess): the backward needs no caller-provided work buffer any more.  Kept for ABI stability.
+extern "C" size_t gsicp_raster_backward_work_bytes(int P) { (void)P; return 0; }
 
 extern "C" int gsicp_raster_backward(const gsicp_raster_args* args, int num_rendered, const int32_t* d_radii,
                                      const void* d_geom, const void* d_binning, const void* d_image,
@@ -580,15 +703,17 @@ extern "C" int gsicp_raster_backward(const gsicp_raster_args* args, int num_rend
                                      float* d_dL_dcolors, float* d_dL_dopacity, float* d_dL_dmeans3D, float* d_dL_dcov3D,
                                      float* d_dL_dsh, float* d_dL_dscales, float* d_dL_drotations, void* d_work,
                                      void* stream_v) {
+  (void)d_work;
   if (!args) return GSICP_EINVAL;
   const int P = args->P, W = args->width, H = args->height;
   if (P == 0) return GSICP_OK;
-  if (!d_geom || !d_binning || !d_image || !d_work || !d_radii) {
+  if (!d_geom || !d_binning || !d_image || !d_radii) {
     set_error("gsicp_raster_backward: null state buffer");
     return GSICP_EINVAL;
   }
-  if (((uintptr_t)d_work & 15) != 0) {
-    set_error("gsicp_raster_backward: d_work must be 16-byte aligned");
+  if (!d_dL_dmeans2D || !d_dL_dcolors || !d_dL_dopacity || !d_dL_dmeans3D || !d_dL_dcov3D || !d_dL_dscales ||
+      !d_dL_drotations || (args->M > 0 && args->d_shs && !d_dL_dsh)) {
+    set_error("gsicp_raster_backward: null gradient buffer");
     return GSICP_EINVAL;
   }
   cudaStream_t stream = (cudaStream_t)stream_v;
@@ -598,16 +723,17 @@ extern "C" int gsicp_raster_backward(const gsicp_raster_args* args, int num_rend
   GeomState geom = GeomState::from((char*)d_geom, P);
   BinState bin = BinState::from((char*)d_binning, num_rendered);
   ImgState img = ImgState::from((char*)d_image, (size_t)W * H, tiles);
-  float* work = (float*)d_work;
+  float* work = geom.moments;  // [P][12]
 
   if (num_rendered > 0) {
+    if (int e = ensure_bwd_smem_attr()) return e;
     ProfScope ps(kProfRenderBwd, stream);
     if (g_render_cull) {
-      GSICP_LAUNCH(render_backward_kernel<true>, tiles, kTilePixels, 0, stream, img.tile_order, img.ranges, bin.point_list, W, H, tiles_x,
+      GSICP_LAUNCH(render_backward_kernel<true>, tiles, kTilePixels, sizeof(BwdSmem), stream, img.tile_order, img.ranges, bin.point_list, W, H, tiles_x,
                    args->d_background, geom.splats, img.final_T, img.n_contrib, d_dL_dout_color, d_dL_dout_depth, work,
                    shard_count, shard_index);
     } else {
-      GSICP_LAUNCH(render_backward_kernel<false>, tiles, kTilePixels, 0, stream, img.tile_order, img.ranges, bin.point_list, W, H, tiles_x,
+      GSICP_LAUNCH(render_backward_kernel<false>, tiles, kTilePixels, sizeof(BwdSmem), stream, img.tile_order, img.ranges, bin.point_list, W, H, tiles_x,
                    args->d_background, geom.splats, img.final_T, img.n_contrib, d_dL_dout_color, d_dL_dout_depth, work,
                    shard_count, shard_index);
     }

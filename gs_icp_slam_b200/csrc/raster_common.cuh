@@ -155,6 +155,15 @@ __device__ __forceinline__ void tile_rect(float px, float py, int radius, int ti
   y1 = min(tiles_y, max(0, (int)((py + radius + kTile - 1) / kTile)));
 }
 
+// 16-byte asynchronous global -> shared copies (LDGSTS): the gather of the 48-B splat records into the staging ring does
+// not pass through registers, so the loads of batch k+1 are in flight while batch k is blended.
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
 // Sub-tile culling shared by the forward and backward render kernels.
 // A tile instance contributes to pixel p iff power(p) = -q(p - c) <= 0 and opacity * exp(power) >= 1/255, i.e.
 // q(p - c) <= tau := ln(255 * opacity), with q(d) = 0.5 (A dx^2 + C dy^2) + B dx dy (the conic).  The warp's pixels lie
@@ -215,13 +224,16 @@ __host__ inline T* carve(char*& p, size_t count) {
   return r;
 }
 
-struct GeomState {   // kept for backward: 49 B / Gaussian
+struct GeomState {   // kept for backward: 97 B / Gaussian
   Splat* splats;     // [P]
+  float* moments;    // [P][12] render-backward moments (raster_backward.cu); preprocess zeroes the rows of the visible
+                     // Gaussians, the per-Gaussian backward kernel consumes and re-zeroes them: no P-sized fill launch
   uint8_t* clamped;  // [P] bit c set <=> SH colour channel c was clamped at 0
-  static size_t bytes(size_t P) { return 128 + P * sizeof(Splat) + 128 + P; }
+  static size_t bytes(size_t P) { return 3 * 128 + P * sizeof(Splat) + P * 12 * sizeof(float) + P; }
   static GeomState from(char* p, size_t P) {
     GeomState g;
     g.splats = carve<Splat>(p, P);
+    g.moments = carve<float>(p, P * 12);
     g.clamped = carve<uint8_t>(p, P);
     return g;
   }

@@ -64,7 +64,8 @@ struct PreArgs {
 // Per-Gaussian part of preprocess.  Returns true (and the tile rectangle) when the Gaussian is visible.
 __device__ __forceinline__ bool preprocess_one(const PreArgs& a, int idx, int32_t* __restrict__ radii,
                                                uint8_t* __restrict__ is_used, Splat* __restrict__ splats,
-                                               uint8_t* __restrict__ clamped, int& x0, int& y0, int& x1, int& y1) {
+                                               float* __restrict__ moments, uint8_t* __restrict__ clamped, int& x0,
+                                               int& y0, int& x1, int& y1) {
   radii[idx] = 0;
   is_used[idx] = 0;
 
@@ -125,6 +126,9 @@ __device__ __forceinline__ bool preprocess_one(const PreArgs& a, int idx, int32_
   s.b = make_float4(conz, a.opac[idx], czx, cyz);
   s.c = make_float4(rgb.x, rgb.y, rgb.z, pv.z);
   splats[idx] = s;
+  // the render-backward accumulators of this Gaussian start at zero (GeomState::moments)
+  float4* mz = reinterpret_cast<float4*>(moments) + 3 * (size_t)idx;
+  mz[0] = mz[1] = mz[2] = make_float4(0.f, 0.f, 0.f, 0.f);
   radii[idx] = (int)my_radius;
   is_used[idx] = 1;
   return true;
@@ -164,10 +168,11 @@ __device__ __forceinline__ uint32_t for_each_owned_tile(bool vis, int x0, int y0
 
 __global__ void __launch_bounds__(256)
 preprocess_kernel(PreArgs a, int32_t* __restrict__ radii, uint8_t* __restrict__ is_used, Splat* __restrict__ splats,
-                  uint8_t* __restrict__ clamped, uint32_t* __restrict__ tiles_touched, uint32_t* __restrict__ tile_count) {
+                  float* __restrict__ moments, uint8_t* __restrict__ clamped, uint32_t* __restrict__ tiles_touched,
+                  uint32_t* __restrict__ tile_count) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // blockDim is a multiple of 32: whole warps stay together
   int x0 = 0, y0 = 0, x1 = 0, y1 = 0;
-  const bool vis = (idx < a.P) && preprocess_one(a, idx, radii, is_used, splats, clamped, x0, y0, x1, y1);
+  const bool vis = (idx < a.P) && preprocess_one(a, idx, radii, is_used, splats, moments, clamped, x0, y0, x1, y1);
   // count this Gaussian in every tile it touches that this rank owns (tile % shard_count == shard_index)
   const uint32_t n = for_each_owned_tile(vis, x0, y0, x1, y1, a.tiles_x, a.shard_count, a.shard_index, 0ull,
                                          [&](unsigned long long, int t) { atomicAdd(&tile_count[t], 1u); });
@@ -341,7 +346,7 @@ render_forward_kernel(const uint32_t* __restrict__ tile_order, const uint2* __re
   const float pxf = (float)px, pyf = (float)py;
 
   // double-buffered staging of 256 instances: one barrier per batch, loads of batch k+1 overlap the blending of batch k
-  __shared__ float4 sA2[2][kTilePixels], sB2[2][kTilePixels], sC2[2][kTilePixels];
+  __shared__ __align__(16) float4 sA2[2][kTilePixels], sB2[2][kTilePixels], sC2[2][kTilePixels];
 
   const uint2 range = ranges[tile];
   const int total = (int)(range.y - range.x);
@@ -354,15 +359,18 @@ render_forward_kernel(const uint32_t* __restrict__ tile_order, const uint2* __re
     if (tid < n) {
       const uint32_t g = point_list[range.x + base + tid];
       const Splat* sp = splats + g;
-      sA2[buf][tid] = __ldg(&sp->a);
-      sB2[buf][tid] = __ldg(&sp->b);
-      sC2[buf][tid] = __ldg(&sp->c);
+      cp_async16(&sA2[buf][tid], &sp->a);
+      cp_async16(&sB2[buf][tid], &sp->b);
+      cp_async16(&sC2[buf][tid], &sp->c);
     }
+    cp_async_commit();
   };
   if (total > 0) stage(0, 0);
 
   for (int base = 0, buf = 0; base < total; base += kTilePixels, buf ^= 1) {
-    // barrier: batch `base` is staged and every warp is done with the other buffer; also the block-wide early exit
+    // barrier: batch `base` is staged (each thread's asynchronous copies have landed) and every warp is done with the
+    // other buffer; also the block-wide early exit
+    cp_async_wait_all();
     if (__syncthreads_count(done) == kTilePixels) break;
     if (base + kTilePixels < total) stage(base + kTilePixels, buf ^ 1);
     const int n = min(kTilePixels, total - base);
@@ -525,8 +533,8 @@ extern "C" int gsicp_raster_forward(const gsicp_raster_args* args, float* d_out_
     pa.prefiltered = args->prefiltered; pa.shard_count = shard_count; pa.shard_index = shard_index;
     {
       ProfScope ps(kProfPreprocess, stream);
-      GSICP_LAUNCH(preprocess_kernel, (P + 255) / 256, 256, 0, stream, pa, d_radii, d_is_used, geom.splats, geom.clamped,
-                   tiles_touched, tile_count);
+      GSICP_LAUNCH(preprocess_kernel, (P + 255) / 256, 256, 0, stream, pa, d_radii, d_is_used, geom.splats, geom.moments,
+                   geom.clamped, tiles_touched, tile_count);
     }
     if (args->debug) GSICP_CUDA(cudaStreamSynchronize(stream));
 

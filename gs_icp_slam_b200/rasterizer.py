@@ -209,15 +209,15 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
     H, W = dL_dout_color.size(1), dL_dout_color.size(2)
     M = sh.size(1) if sh.numel() != 0 else 0
     with _on_device(dev):
-        # One zero-filled slab for the eight gradient tensors and the work buffer (one fill launch instead of nine).  The
-        # kernels are launched from raw offsets into it; the tensor views are made afterwards, while the GPU is busy.
+        # One UNINITIALISED slab for the eight gradient tensors: the per-Gaussian backward kernel writes every element
+        # (zeros for Gaussians outside the view), so no fill launch precedes it.  The kernels are launched from raw offsets
+        # into it; the tensor views are made afterwards, while the GPU is busy.
         sizes = (3 * P, 3 * P, NUM_CHANNELS * P, P, 6 * P, 3 * M * P, 3 * P, 4 * P)
         offs, off = [], 0
         for n in sizes:
             offs.append(off)
             off += (n + 3) // 4 * 4  # keep every view 16-byte aligned
-        work_n = (int(lib.gsicp_raster_backward_work_bytes(P)) // 4) if P != 0 else 0
-        slab = torch.zeros(off + work_n, dtype=torch.float32, device=dev)
+        slab = (torch.empty if P != 0 else torch.zeros)(max(off, 1), dtype=torch.float32, device=dev)
         if P != 0:
             base = slab.data_ptr()
             p3d, p2d, pcol, popa, pcov, psh, psc, prot = (base + 4 * o for o in offs)
@@ -230,7 +230,7 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
             check(
                 lib.gsicp_raster_backward(C.byref(args), int(R), radii_c.data_ptr(), geomBuffer.data_ptr(),
                                           binningBuffer.data_ptr(), imageBuffer.data_ptr(), ptrs[11], ptrs[12], p2d, pcol, popa,
-                                          p3d, pcov, psh if M != 0 else None, psc, prot, base + 4 * off, stream),
+                                          p3d, pcov, psh if M != 0 else None, psc, prot, None, stream),
                 "gsicp_raster_backward")
             del keep
         shapes = ((P, 3), (P, 3), (P, NUM_CHANNELS), (P, 1), (P, 6), (P, M, 3), (P, 3), (P, 4))

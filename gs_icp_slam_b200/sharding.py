@@ -54,13 +54,23 @@ class DevicePtrArray:
         self.__cuda_array_interface__ = {"shape": (int(count),), "typestr": typestr, "data": (int(ptr), False), "version": 3}
 
 
+def _lib_stream(stream, device):
+    """torch view of the cudaStream_t the library passed to a collective callback (0 = the legacy default stream): the
+    collective must be ordered after the kernels on THAT stream and before the library's readback on it, not on torch's
+    current stream of the calling thread."""
+    if not stream or not torch.cuda.is_available():
+        return torch.cuda.default_stream(device) if torch.cuda.is_available() else None
+    return torch.cuda.ExternalStream(int(stream), device=device)
+
+
 def make_gicp_allreduce(device, group=None):
     """Callback for FastGICP.set_shard: all-reduces the library's fp64 buffer in place over `group`."""
     import torch.distributed as dist
 
     def cb(ptr, count, stream):
         t = torch.as_tensor(DevicePtrArray(ptr, count), device=device)
-        dist.all_reduce(t, group=group)
+        with torch.cuda.stream(_lib_stream(stream, device)):  # the stream the library launched its kernels on
+            dist.all_reduce(t, group=group)
 
     return cb
 
@@ -71,6 +81,54 @@ def make_raster_allreduce(device, group=None):
 
     def cb(ptr, count, stream):
         t = torch.as_tensor(DevicePtrArray(ptr, count, "<f4"), device=device)
-        dist.all_reduce(t, group=group)
+        with torch.cuda.stream(_lib_stream(stream, device)):
+            dist.all_reduce(t, group=group)
 
     return cb
+
+
+class ShardGroup:
+    """One rank's membership of a sharded run: wires the rasterizer (tile shards + moments exchange) and FastGICP objects
+    (source-point shards + normal-equation exchange) to the collective.  Collective = torch.distributed all-reduce
+    reached through the library's callbacks, ordered on the library's stream (the callbacks receive the stream
+    the kernels were launched on)."""
+
+    def __init__(self, device, world, rank, group=None):
+        self.device, self.world, self.rank, self.group = device, world, rank, group
+        self._gicp = []
+        self._raster = False
+
+    def _allreduce(self, typestr):
+        import torch.distributed as dist
+
+        dev, group = self.device, self.group
+
+        def cb(ptr, count, stream):
+            t = torch.as_tensor(DevicePtrArray(ptr, count, typestr), device=dev)
+            with torch.cuda.stream(_lib_stream(stream, dev)):  # after the kernels on the library's stream, before its readback
+                dist.all_reduce(t, group=group)
+
+        return cb
+
+    def attach_rasterizer(self):
+        from . import rasterizer
+
+        rasterizer.set_tile_shard(self.world, self.rank)
+        rasterizer.set_allreduce(self._allreduce("<f4"))
+        self._raster = True
+
+    def attach_gicp(self, reg):
+        reg.set_shard(self.world, self.rank, self._allreduce("<f8"))
+        self._gicp.append(reg)
+
+    def describe(self):
+        return "NCCL all-reduce (torch.distributed) of the 28-double normal equations / the [V][12] render moments on the library's stream"
+
+    def close(self):
+        if self._raster:
+            from . import rasterizer
+
+            rasterizer.set_tile_shard(1, 0)
+            rasterizer.set_allreduce(None)
+            self._raster = False
+        self._gicp = []

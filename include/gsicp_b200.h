@@ -95,11 +95,12 @@ int gsicp_raster_forward(const gsicp_raster_args* args,
 
 /* Backward.  Replaces RasterizeGaussiansBackwardCUDA -> Rasterizer::backward
  * (DGR/rasterize_points.cu:123-206, rasterizer_impl.cu:351-454).
- * All gradient outputs are device buffers that the caller ZERO-fills
- * (rasterize_points.cu:158-167): dL_dmeans2D[P,3], dL_dcolors[P,3], dL_dopacity[P],
- * dL_dmeans3D[P,3], dL_dcov3D[P,6], dL_dsh[P,M,3], dL_dscales[P,3], dL_drotations[P,4].
- * d_work must hold gsicp_raster_backward_work_bytes(P) zero-filled bytes (the reference's
- * dL_dconic[P,6] + dL_ddepths[P] scratch). */
+ * Gradient outputs are caller-allocated device buffers which need NOT be initialised — every element is written,
+ * zeros for Gaussians outside the view (the reference zero-fills ten P-sized tensors first, rasterize_points.cu:158-167):
+ * dL_dmeans2D[P,3], dL_dcolors[P,3], dL_dopacity[P], dL_dmeans3D[P,3], dL_dcov3D[P,6], dL_dsh[P,M,3], dL_dscales[P,3],
+ * dL_drotations[P,4].  The per-Gaussian scratch of the reference (dL_dconic[P,6] + dL_ddepths[P]) lives in the geometry
+ * buffer of the forward pass: d_work is ignored (may be NULL) and gsicp_raster_backward_work_bytes() returns 0; both
+ * are kept so that round-1 callers keep linking. */
 size_t gsicp_raster_backward_work_bytes(int P);
 /* Multi-GPU (tile-sharded rendering): when set and tile_shard_count > 1, gsicp_raster_backward sums the 12
  * render moments of the visible Gaussians over the ranks through this callback (in place, fp32, on `stream`) between

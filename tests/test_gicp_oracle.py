@@ -166,7 +166,9 @@ def test_linearize_matches_eigen_per_point(eig):
     # correspondences: brute force with the same fp32 transform
     Pf = pose.astype(np.float32)
     s32, t32 = src.astype(np.float32), tgt.astype(np.float32)
-    tp = ((Pf[:3, 0] * s32[:, [0]] + Pf[:3, 1] * s32[:, [1]]) + Pf[:3, 2] * s32[:, [2]]) + Pf[:3, 3]
+    # (c0 x + c1 y) + (c2 z + c3): the order Eigen's packet product evaluates trans_f * getVector4fMap() (fgi:260), pinned
+    # against the reference build in tests/test_gicp_reference.py
+    tp = (Pf[:3, 0] * s32[:, [0]] + Pf[:3, 1] * s32[:, [1]]) + (Pf[:3, 2] * s32[:, [2]] + Pf[:3, 3])
     d = (tp[:, None, :] - t32[None, :, :]).astype(np.float32) ** 2
     d2 = (d[..., 0] + d[..., 1]) + d[..., 2]
     assert np.array_equal(corr, np.where(d2.min(1) < 0.25, d2.argmin(1), -1))

@@ -1,37 +1,20 @@
-"""Large-config scaling benches (BASELINE configs C4 and C5), one process per GPU under torchrun:
-  C4: 1280x960, 1M Gaussians, rasterizer fwd+bwd only, tiles sharded over the ranks, gradient all-reduce
-  C5: GICP on a 2M x 2M point pair, source points sharded, all-reduce of the 28-double normal equations
-    python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tools/bench_large.py [c4|c5] [iters]
-Prints one JSON line per config (rank 0): ms per iteration (max over ranks) — strong scaling, total work fixed."""
+"""Large strong-scaling configs of bench.py (`--config c4|c5`), one process per GPU under torchrun:
+  C4: 1280x960, 1M Gaussians, rasterizer fwd+bwd only, tiles sharded over the ranks (moments exchange inside backward)
+  C5: GICP align on a 2M x 2M point pair, source points sharded (28-double normal equations exchanged per linearize)
+Total work is fixed as N grows ("scaling": "strong").  A step = one raster fwd+bwd iteration (C4) / one align() (C5).
+Same JSON contract as the default config: W warm-up steps, K steps timed with CUDA events between barriers, max over ranks.
+    python bench.py --config c4 [--gpus N --steps K --warmup W]      (torchrun for N > 1)"""
 import json
 import os
-import sys
 import time
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np  # noqa: E402
-import torch  # noqa: E402
-import torch.distributed as dist  # noqa: E402
-
-from gs_icp_slam_b200 import rasterizer as R  # noqa: E402
-from gs_icp_slam_b200 import sharding  # noqa: E402
-from gs_icp_slam_b200 import synthetic as S  # noqa: E402
-
-rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
-local = int(os.environ.get("LOCAL_RANK", 0))
-torch.cuda.set_device(local)
-dev = torch.device("cuda", local)
-if world > 1:
-    dist.init_process_group("nccl", device_id=dev)
-which = sys.argv[1] if len(sys.argv) > 1 else "c4"
-iters = int(sys.argv[2]) if len(sys.argv) > 2 else 10
+import numpy as np
 
 
-def timed(fn, iters, warm=3):
-    for _ in range(warm):
-        fn()
+def _timed(fn, steps, warmup, world, dev, torch, dist, flush):
     ts = []
-    for _ in range(iters):
+    for i in range(warmup + steps):
+        flush.fill_(i & 0xff)  # L2 flush between steps, outside the timed events
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -40,112 +23,123 @@ def timed(fn, iters, warm=3):
         fn()
         e1.record()
         torch.cuda.synchronize()
-        t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ts.append(float(t.item()))
-    return float(np.median(ts))
-
-
-if which == "c4":
-    from diff_gaussian_rasterization import GaussianRasterizationSettings, GaussianRasterizer
-
-    W, H, P = 1280, 960, 1000000
-    cam = dict(S.TUM)
-    cam.update(W=W, H=H, fx=cam["fx"] * 2, fy=cam["fy"] * 2, cx=cam["cx"] * 2, cy=cam["cy"] * 2)
-    g = S.gaussian_map(P, 4, scale=2.0)
-    cm = S.camera_matrices(S.trajectory_pose(3, 20, scale=2.0), cam)
-    t = {k: torch.from_numpy(v).to(dev).requires_grad_(True) for k, v in g.items()}
-    c = {k: (torch.from_numpy(v).to(dev) if isinstance(v, np.ndarray) else v) for k, v in cm.items()}
-    m2 = torch.zeros_like(t["means3D"], requires_grad=True)
-    gen = torch.Generator(device="cpu").manual_seed(5)
-    gcol, gdep = torch.randn((3, H, W), generator=gen).to(dev), torch.randn((1, H, W), generator=gen).to(dev)
-    R.set_tile_shard(world, rank)
-    cb_time = [0.0, 0]
+        if i >= warmup:
+            ts.append(e0.elapsed_time(e1))
+    t = torch.tensor([float(np.sum(ts))], device=dev, dtype=torch.float64)
     if world > 1:
-        inner = sharding.make_raster_allreduce(dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item()), ts
 
-        def timed_cb(ptr, count, stream):
-            t0 = time.perf_counter()
-            inner(ptr, count, stream)
-            cb_time[0] += time.perf_counter() - t0
-            cb_time[1] = count
 
-        R.set_allreduce(timed_cb)
-    mask = sharding.tile_owner_mask(H, W, world, rank, dev)
-    rs = GaussianRasterizationSettings(H, W, c["tanfovx"], c["tanfovy"], torch.zeros(3, device=dev), 1.0, c["viewmatrix"],
-                                       c["projmatrix"], 0, c["campos"], False, False)
-    info = {}
+def main(args, rank, local_rank, world):
+    import torch
 
-    def it():
-        depth, color, radii, used = GaussianRasterizer(rs)(means3D=t["means3D"], means2D=m2, opacities=t["opacities"],
-                                                           shs=t["shs"], scales=t["scales"], rotations=t["rotations"])
-        info["R"] = color.grad_fn.num_rendered
-        ((color * gcol * mask).sum() + (depth * gdep * mask).sum()).backward()
-        for k in t:
-            t[k].grad = None
-        m2.grad = None
+    from gs_icp_slam_b200 import _lib, sharding
+    from gs_icp_slam_b200 import synthetic as S
 
-    ms = timed(it, iters)
-    from gs_icp_slam_b200 import _lib
+    if args.impl == "reference":
+        if rank == 0:
+            print(json.dumps({"impl": "reference", "unavailable": "the large configs have no reference arm: the reference's "
+                              "rasterizer / fast_gicp are single-device (SURVEY §8e); see the default config"}))
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
 
+        dist.init_process_group("nccl", device_id=dev)
+    K, Wm = args.steps, args.warmup
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    group = sharding.ShardGroup(dev, world, rank) if world > 1 else None
+    extra = {}
+    if args.config == "c4":
+        from diff_gaussian_rasterization import GaussianRasterizationSettings, GaussianRasterizer
+        from gs_icp_slam_b200 import rasterizer as R
+
+        W, H, P = 1280, 960, args.gaussians
+        cam = dict(S.TUM)
+        cam.update(W=W, H=H, fx=cam["fx"] * 2, fy=cam["fy"] * 2, cx=cam["cx"] * 2, cy=cam["cy"] * 2)
+        g = S.gaussian_map(P, 4, scale=2.0)
+        cm = S.camera_matrices(S.trajectory_pose(3, 20, scale=2.0), cam)
+        t = {k: torch.from_numpy(v).to(dev).requires_grad_(True) for k, v in g.items()}
+        c = {k: (torch.from_numpy(v).to(dev) if isinstance(v, np.ndarray) else v) for k, v in cm.items()}
+        m2 = torch.zeros_like(t["means3D"], requires_grad=True)
+        gen = torch.Generator(device="cpu").manual_seed(5)
+        gcol, gdep = torch.randn((3, H, W), generator=gen).to(dev), torch.randn((1, H, W), generator=gen).to(dev)
+        if group is not None:
+            group.attach_rasterizer()
+        mask = sharding.tile_owner_mask(H, W, world, rank, dev)
+        rs = GaussianRasterizationSettings(H, W, c["tanfovx"], c["tanfovy"], torch.zeros(3, device=dev), 1.0, c["viewmatrix"],
+                                           c["projmatrix"], 0, c["campos"], False, False)
+        info = {}
+
+        def it():
+            depth, color, radii, used = GaussianRasterizer(rs)(means3D=t["means3D"], means2D=m2, opacities=t["opacities"],
+                                                               shs=t["shs"], scales=t["scales"], rotations=t["rotations"])
+            info["R"] = color.grad_fn.num_rendered
+            ((color * gcol * mask).sum() + (depth * gdep * mask).sum()).backward()
+            for k in t:
+                t[k].grad = None
+            m2.grad = None
+
+        metric, unit = "rasterizer fwd+bwd iterations/sec (1280x960, 1M Gaussians)", "iterations/s"
+        workload = f"C4: 1280x960, {P} Gaussians (seed 4), rasterizer forward + backward with N(0,1) image gradients"
+        step = it
+        extra["tile_instances_this_rank"] = lambda: info.get("R")
+    else:
+        import pygicp
+
+        n = args.gaussians
+        tgt, src, T = S.gicp_pair(n, n, 6, 7, 0.001, scale=5.0)
+        reg = pygicp.FastGICP()
+        reg.set_max_correspondence_distance(0.25)
+        reg.set_max_knn_distance(99999)
+        if group is not None:
+            group.attach_gicp(reg)
+        reg.set_input_target(tgt)
+        reg.calculate_target_covariance()
+        src_dev = torch.from_numpy(src.astype(np.float32)).to(dev)
+        res = {}
+
+        def it():
+            reg.set_input_source(src_dev)   # new frame: source covariances are recomputed inside align (fgi:229-232)
+            res["pose"] = reg.align(np.eye(4, dtype=np.float32))
+
+        metric, unit = "GICP align/sec (2M x 2M points)", "aligns/s"
+        workload = f"C5: GICP align of a {n} x {n} point pair (seeds 6/7), k-NN source covariances + LM loop, max_corr 0.25"
+        step = it
+        extra["lm_iterations"] = lambda: reg.last_iterations
+        extra["pose_error_vs_ground_truth"] = lambda: float(np.abs(res["pose"].astype(np.float64) - T).max())
+
+    for _ in range(2):  # allocator / scratch growth, untimed
+        step()
+    t_ms, ts = _timed(step, K, Wm, world, dev, torch, dist, flush)
     _lib.prof_reset()
     _lib.prof_enable(True)
-    for _ in range(iters):
-        it()
+    for _ in range(min(K, 5)):
+        step()
     torch.cuda.synchronize()
     _lib.prof_enable(False)
-    kern = {k: round(v[0] / max(v[1], 1) * 1e3, 1) for k, v in _lib.prof_read().items() if v[1]}
-    # phase split (forward / loss + backward), host-timed with a sync on both sides
-    ph = {"fwd": 0.0, "bwd": 0.0}
-    cb_time[0] = 0.0
-    for _ in range(iters):
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        depth, color, radii, used = GaussianRasterizer(rs)(means3D=t["means3D"], means2D=m2, opacities=t["opacities"],
-                                                           shs=t["shs"], scales=t["scales"], rotations=t["rotations"])
-        torch.cuda.synchronize()
-        t1 = time.perf_counter()
-        ((color * gcol * mask).sum() + (depth * gdep * mask).sum()).backward()
-        torch.cuda.synchronize()
-        t2 = time.perf_counter()
-        ph["fwd"] += (t1 - t0) * 1e3 / iters
-        ph["bwd"] += (t2 - t1) * 1e3 / iters
-        for k in t:
-            t[k].grad = None
-        m2.grad = None
+    kern = {k: {"ms_per_launch": v[0] / v[1], "launches_per_step": v[1] / min(K, 5)} for k, v in _lib.prof_read().items() if v[1]}
     if rank == 0:
-        print(json.dumps({"kernels_us": kern, "phase_ms": ph, "allreduce_cb_ms": cb_time[0] * 1e3 / iters,
-                          "allreduce_floats": cb_time[1]}))
-        print(json.dumps({"config": "C4 1280x960, 1M Gaussians, raster fwd+bwd, tile-sharded", "n_gpus": world, "ms_per_iter": ms,
-                          "iters_per_s": 1e3 / ms, "tile_instances_this_rank": info["R"]}))
-else:
-    import pygicp
-
-    n = int(os.environ.get("C5_POINTS", 2000000))
-    tgt, src, T = S.gicp_pair(n, n, 6, 7, 0.001, scale=5.0)
-    reg = pygicp.FastGICP()
-    reg.set_max_correspondence_distance(0.25)
-    reg.set_max_knn_distance(99999)
+        out = {"metric": metric, "value": K / (t_ms * 1e-3), "unit": unit, "n_gpus": world, "steps": K, "warmup": Wm,
+               "ms_per_step": t_ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+               "dtype": "f32 (rasterizer)" if args.config == "c4" else "f64 (GICP algebra on f32 points)", "data": "synthetic",
+               "config": {"workload": workload, "l2": "256 MiB write between steps, excluded from the per-step CUDA-event time"},
+               "parallelism": "single GPU" if world == 1 else (f"{world} GPUs: " + ("screen tiles" if args.config == "c4" else "source points") +
+                                                                " sharded, " + (group.describe() if group else "")),
+               "ms_p50_max": [float(np.median(ts)), float(np.max(ts))], "kernels": kern,
+               "e2e": {"value": K / (t_ms * 1e-3), "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 64,
+                       "note": "the public API call is what is timed; inputs are device tensors of the caller (the mapper's "
+                               "parameters / the tracker's cloud), results (loss gradient tensors / 4x4 pose) stay where the API puts them"}}
+        for k, f in extra.items():
+            out[k] = f()
+        print(json.dumps(out))
+    if group is not None:
+        group.close()
     if world > 1:
-        reg.set_shard(world, rank, sharding.make_gicp_allreduce(dev))
-    reg.set_input_target(tgt)
-    reg.calculate_target_covariance()
-    reg.set_input_source(src)
-    reg.calculate_source_covariance()
-    pose = np.eye(4)
-    res = {}
-
-    def it():
-        res["H"], res["b"], res["e"] = reg.linearize(pose)
-
-    ms = timed(it, iters)
-    t0 = time.time()
-    out = reg.align(np.eye(4))
-    dt = (time.time() - t0) * 1e3
-    if rank == 0:
-        print(json.dumps({"config": f"C5 GICP {n}x{n} points, source-sharded", "n_gpus": world, "linearize_ms": ms,
-                          "align_ms": dt, "lm_iterations": reg.last_iterations, "pose_err": float(np.abs(out - T).max())}))
-if world > 1:
-    dist.barrier()
-    dist.destroy_process_group()
+        dist.barrier()
+        dist.destroy_process_group()

@@ -1,4 +1,7 @@
-"""Summarise an ncu report (--set full) as text for profiles/:  python tools/ncu_summary.py gpurun_out/x.ncu-rep > profiles/x.txt"""
+"""Summarise an ncu report (--set full) as text for profiles/:  python tools/ncu_summary.py gpurun_out/x.ncu-rep > profiles/x.txt
+With `--traffic profiles/ncu_traffic.json [tag]` the per-launch DRAM bytes and warp-instruction counts of this repo's hot
+kernels are also written to the JSON file bench.py reads for `roofline.traffic` (mean over the captured launches)."""
+import json
 import csv
 import io
 import subprocess
@@ -35,19 +38,59 @@ KEYS = [
 ]
 
 
-def main(path):
+TRAFFIC_KERNELS = {"render_backward_kernel": "render_backward", "render_forward_kernel": "render_forward",
+                   "gaussian_backward_kernel": "gaussian_backward", "preprocess_kernel": "preprocess", "tile_sort_kernel": "tile_sort",
+                   "align_lm_kernel": "gicp_align", "linearize_kernel": "gicp_linearize", "knn_kernel": "gicp_covariance"}
+
+
+def num(x):
+    try:
+        return float(x.replace(",", ""))
+    except Exception:
+        return None
+
+
+def main(path, traffic_path=None, tag=""):
     raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     head, units = rows[0], rows[1]
     print(f"# {path}: ncu --set full --clock-control none --import-source on (one row per profiled launch)")
+    acc = {}
     for r in rows[2:]:
         d = dict(zip(head, r))
         u = dict(zip(head, units))
+        for frag, name in TRAFFIC_KERNELS.items():
+            if frag in d["Kernel Name"]:
+                scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+                rd, wr = num(d.get("dram__bytes_read.sum", "")), num(d.get("dram__bytes_write.sum", ""))
+                if rd is not None and wr is not None:
+                    b = rd * scale.get(u.get("dram__bytes_read.sum", "byte"), 1.0) + wr * scale.get(u.get("dram__bytes_write.sum", "byte"), 1.0)
+                    a = acc.setdefault(name, {"dram": [], "inst": []})
+                    a["dram"].append(b)
+                    i = num(d.get("smsp__inst_executed.sum", ""))
+                    if i is not None:
+                        a["inst"].append(i)
         print(f"\n== {d['Kernel Name'][:110]}")
         for k, label in KEYS:
             if k in d and d[k] != "":
                 print(f"   {label:34s} {d[k]:>16s} {u.get(k, '')}")
 
 
+    if traffic_path:
+        try:
+            out = json.load(open(traffic_path))
+        except Exception:
+            out = {}
+        for name, a in acc.items():
+            out[name] = {"dram_bytes": sum(a["dram"]) / len(a["dram"]),
+                         "warp_instructions": (sum(a["inst"]) / len(a["inst"])) if a["inst"] else None,
+                         "launches": len(a["dram"]),
+                         "source": f"ncu --set full --clock-control none, dram__bytes_read.sum + dram__bytes_write.sum per launch ({tag or path})"}
+        json.dump(out, open(traffic_path, "w"), indent=1, sort_keys=True)
+
+
 if __name__ == "__main__":
-    main(sys.argv[1])
+    if len(sys.argv) > 3 and sys.argv[2] == "--traffic":
+        main(sys.argv[1], sys.argv[3], sys.argv[4] if len(sys.argv) > 4 else "")
+    else:
+        main(sys.argv[1])
