@@ -750,9 +750,9 @@ def main():
         alg = {  # algorithmic bytes per launch (SURVEY.md §8d / DESIGN.md §5)
             "render_forward": 8 * tiles + 52 * R + 36 * npix,
             "render_backward": 8 * tiles + 52 * R + 36 * npix + 56 * V,
-            "gicp_linearize": 60 * n_src + 60 * n_corr + 12 * n_tgt + 224,
+            # one launch of the device-resident LM loop = n_lin x (linearize + >= 1 compute_error) (SURVEY §8d per-call figures)
+            "gicp_linearize": (st_p["n_lin"] / K) * ((60 * n_src + 60 * n_corr + 12 * n_tgt + 224) + (12 * n_src + 60 * n_corr + 8)),
             "gicp_error": 12 * n_src + 60 * n_corr + 8,
-            "gicp_align": 0,
             "preprocess": 56 * P + 5 * P + 79 * V,
             "gaussian_backward": V * 139 + P * 64,
             "tile_sort": 12 * R,

@@ -83,6 +83,7 @@ _sig("gsicp_raster_backward", i32, [C.POINTER(RasterArgs), i32, vp, vp, vp, vp, 
 _sig("gsicp_raster_export_binning", i32, [C.POINTER(RasterArgs), i32, vp, vp, vp, vp, vp])
 _sig("gsicp_mark_visible", i32, [i32, vp, vp, vp, vp, vp])
 _sig("gsicp_test_set_render_cull", None, [i32])
+_sig("gsicp_test_set_bwd_variant", None, [i32])
 _sig("gsicp_dist2", i32, [i32, vp, vp, vp])
 
 _sig("gsicp_gicp_create", vp, [])
@@ -119,6 +120,7 @@ _sig("gsicp_gicp_linearize", i32, [vp, vp, vp, vp, vp])
 _sig("gsicp_gicp_compute_error", i32, [vp, vp, vp])
 _sig("gsicp_gicp_set_shard", i32, [vp, i32, i32, ALLREDUCE_FN, vp])
 _sig("gsicp_gicp_set_stream", i32, [vp, vp])
+_sig("gsicp_gicp_set_host_lm", i32, [vp, i32])
 _sig("gsicp_mapping_loss_work_bytes", C.c_size_t, [i32, i32])
 _sig("gsicp_mapping_loss_forward", i32, [i32, i32, vp, vp, vp, vp, C.c_float, C.c_float, C.c_float, i32, vp, vp, vp, vp, vp])
 _sig("gsicp_mapping_loss_backward", i32, [i32, i32, vp, vp, vp, vp, C.c_float, C.c_float, C.c_float, i32, vp, vp, vp, vp, vp])

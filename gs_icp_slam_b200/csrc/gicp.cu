@@ -350,85 +350,108 @@ __global__ void corr_unpack_kernel(int n, const double* __restrict__ in, int32_t
   sqd[i] = (float)in[(size_t)n + i];
 }
 
-// Mahalanobis + residual/Jacobian + normal-equation reduction (fgi:273-352): one THREAD per source point.
+// Mahalanobis + residual/Jacobian of ONE matched source point i <-> target point j (fgi:273-352): adds the point's 21 H
+// entries (upper triangle, row-major), 6 b entries and its error term to v[28], stores the Mahalanobis matrix.
+__device__ __forceinline__ void linearize_point(const PoseD& T, int i, int j, const float* __restrict__ src_xyz,
+                                                const double* __restrict__ src_cov, const float* __restrict__ tgt_xyz,
+                                                const double* __restrict__ tgt_cov, double* __restrict__ mahal, double* v) {
+  const float px = src_xyz[3 * (size_t)i], py = src_xyz[3 * (size_t)i + 1], pz = src_xyz[3 * (size_t)i + 2];
+  const double* ca = src_cov + 6 * (size_t)i;
+  const double* cb = tgt_cov + 6 * (size_t)j;
+  const double A[3][3] = {{ca[0], ca[1], ca[2]}, {ca[1], ca[3], ca[4]}, {ca[2], ca[4], ca[5]}};
+  // RCR = C_B + R C_A R^T  (fgi:280)
+  double RA[3][3], RCR[3][3];
+#pragma unroll
+  for (int r = 0; r < 3; r++)
+#pragma unroll
+    for (int c = 0; c < 3; c++) RA[r][c] = (T.R[r][0] * A[0][c] + T.R[r][1] * A[1][c]) + T.R[r][2] * A[2][c];
+  const double B[3][3] = {{cb[0], cb[1], cb[2]}, {cb[1], cb[3], cb[4]}, {cb[2], cb[4], cb[5]}};
+#pragma unroll
+  for (int r = 0; r < 3; r++)
+#pragma unroll
+    for (int c = 0; c < 3; c++) RCR[r][c] = B[r][c] + ((RA[r][0] * T.R[c][0] + RA[r][1] * T.R[c][1]) + RA[r][2] * T.R[c][2]);
+  double M[3][3];
+  if (!inverse3(RCR, M)) {
+    // reference: pseudo-inverse via complete orthogonal decomposition (fgi:283-286); a singular
+    // RCR cannot occur with regularised covariances — contribute nothing.
+#pragma unroll
+    for (int r = 0; r < 3; r++)
+#pragma unroll
+      for (int c = 0; c < 3; c++) M[r][c] = 0.0;
+  }
+  double* mo = mahal + 6 * (size_t)i;
+  mo[0] = M[0][0]; mo[1] = M[0][1]; mo[2] = M[0][2]; mo[3] = M[1][1]; mo[4] = M[1][2]; mo[5] = M[2][2];
+  // use the stored (symmetric) representation from here on so linearize and compute_error agree
+  M[1][0] = M[0][1]; M[2][0] = M[0][2]; M[2][1] = M[1][2];
+
+  const double ax = (double)px, ay = (double)py, az = (double)pz;
+  const double qx = ((T.R[0][0] * ax + T.R[0][1] * ay) + T.R[0][2] * az) + T.t[0];
+  const double qy = ((T.R[1][0] * ax + T.R[1][1] * ay) + T.R[1][2] * az) + T.t[1];
+  const double qz = ((T.R[2][0] * ax + T.R[2][1] * ay) + T.R[2][2] * az) + T.t[2];
+  const double e[3] = {(double)tgt_xyz[3 * (size_t)j] - qx, (double)tgt_xyz[3 * (size_t)j + 1] - qy,
+                       (double)tgt_xyz[3 * (size_t)j + 2] - qz};
+  double Me[3];
+#pragma unroll
+  for (int r = 0; r < 3; r++) Me[r] = (M[r][0] * e[0] + M[r][1] * e[1]) + M[r][2] * e[2];
+  v[27] += (e[0] * Me[0] + e[1] * Me[1]) + e[2] * Me[2];
+
+  // J = [S | -I], S = skew(q):  S = [[0,-qz,qy],[qz,0,-qx],[-qy,qx,0]]
+  const double S[3][3] = {{0.0, -qz, qy}, {qz, 0.0, -qx}, {-qy, qx, 0.0}};
+  double MS[3][3];  // M * S
+#pragma unroll
+  for (int r = 0; r < 3; r++)
+#pragma unroll
+    for (int c = 0; c < 3; c++) MS[r][c] = (M[r][0] * S[0][c] + M[r][1] * S[1][c]) + M[r][2] * S[2][c];
+  double H[6][6];
+#pragma unroll
+  for (int r = 0; r < 3; r++)
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      H[r][c] = (S[0][r] * MS[0][c] + S[1][r] * MS[1][c]) + S[2][r] * MS[2][c];  // S^T M S
+      H[r][3 + c] = -((S[0][r] * M[0][c] + S[1][r] * M[1][c]) + S[2][r] * M[2][c]);  // -S^T M
+      H[3 + r][3 + c] = M[r][c];
+    }
+  int o = 0;
+#pragma unroll
+  for (int r = 0; r < 6; r++)
+#pragma unroll
+    for (int c = r; c < 6; c++) v[o++] += H[r][c];
+#pragma unroll
+  for (int r = 0; r < 3; r++) {
+    v[21 + r] += (S[0][r] * Me[0] + S[1][r] * Me[1]) + S[2][r] * Me[2];  // S^T M e
+    v[24 + r] += -Me[r];
+  }
+}
+
+// e^T M e of one matched pair with the cached Mahalanobis matrix (fgi:355-378)
+__device__ __forceinline__ double error_point(const PoseD& T, int i, int j, const float* __restrict__ src_xyz,
+                                              const float* __restrict__ tgt_xyz, const double* __restrict__ mahal) {
+  const double ax = (double)src_xyz[3 * (size_t)i], ay = (double)src_xyz[3 * (size_t)i + 1], az = (double)src_xyz[3 * (size_t)i + 2];
+  const double qx = ((T.R[0][0] * ax + T.R[0][1] * ay) + T.R[0][2] * az) + T.t[0];
+  const double qy = ((T.R[1][0] * ax + T.R[1][1] * ay) + T.R[1][2] * az) + T.t[1];
+  const double qz = ((T.R[2][0] * ax + T.R[2][1] * ay) + T.R[2][2] * az) + T.t[2];
+  const double e[3] = {(double)tgt_xyz[3 * (size_t)j] - qx, (double)tgt_xyz[3 * (size_t)j + 1] - qy,
+                       (double)tgt_xyz[3 * (size_t)j + 2] - qz};
+  // the Mahalanobis matrices are rewritten by other blocks between the phases of the persistent LM kernel: read them
+  // through L2 (ld.global.cg), never from a stale L1 line
+  const double* mp = mahal + 6 * (size_t)i;
+  const double m[6] = {__ldcg(mp), __ldcg(mp + 1), __ldcg(mp + 2), __ldcg(mp + 3), __ldcg(mp + 4), __ldcg(mp + 5)};
+  const double Me0 = (m[0] * e[0] + m[1] * e[1]) + m[2] * e[2];
+  const double Me1 = (m[1] * e[0] + m[3] * e[1]) + m[4] * e[2];
+  const double Me2 = (m[2] * e[0] + m[4] * e[1]) + m[5] * e[2];
+  return (e[0] * Me0 + e[1] * Me1) + e[2] * Me2;
+}
+
+// Normal-equation reduction of the host-driven path: one THREAD per source point.
 __global__ void __launch_bounds__(kLinBlock, 1)
 linearize_kernel(PoseD T, LinArgs a) {
   const int i = a.begin + blockIdx.x * blockDim.x + threadIdx.x;
   double v[kRed];
 #pragma unroll
   for (int k = 0; k < kRed; k++) v[k] = 0.0;
-
   if (i < a.end) {
-    const float px = a.src_xyz[3 * (size_t)i], py = a.src_xyz[3 * (size_t)i + 1], pz = a.src_xyz[3 * (size_t)i + 2];
     const int32_t j = a.corr[i];
-    const bool matched = j >= 0;
-    if (matched) {
-      const double* ca = a.src_cov + 6 * (size_t)i;
-      const double* cb = a.tgt_cov + 6 * (size_t)j;
-      const double A[3][3] = {{ca[0], ca[1], ca[2]}, {ca[1], ca[3], ca[4]}, {ca[2], ca[4], ca[5]}};
-      // RCR = C_B + R C_A R^T  (fgi:280)
-      double RA[3][3], RCR[3][3];
-#pragma unroll
-      for (int r = 0; r < 3; r++)
-#pragma unroll
-        for (int c = 0; c < 3; c++) RA[r][c] = (T.R[r][0] * A[0][c] + T.R[r][1] * A[1][c]) + T.R[r][2] * A[2][c];
-      const double B[3][3] = {{cb[0], cb[1], cb[2]}, {cb[1], cb[3], cb[4]}, {cb[2], cb[4], cb[5]}};
-#pragma unroll
-      for (int r = 0; r < 3; r++)
-#pragma unroll
-        for (int c = 0; c < 3; c++) RCR[r][c] = B[r][c] + ((RA[r][0] * T.R[c][0] + RA[r][1] * T.R[c][1]) + RA[r][2] * T.R[c][2]);
-      double M[3][3];
-      if (!inverse3(RCR, M)) {
-        // reference: pseudo-inverse via complete orthogonal decomposition (fgi:283-286); a singular
-        // RCR cannot occur with regularised covariances — contribute nothing.
-#pragma unroll
-        for (int r = 0; r < 3; r++)
-#pragma unroll
-          for (int c = 0; c < 3; c++) M[r][c] = 0.0;
-      }
-      double* mo = a.mahal + 6 * (size_t)i;
-      mo[0] = M[0][0]; mo[1] = M[0][1]; mo[2] = M[0][2]; mo[3] = M[1][1]; mo[4] = M[1][2]; mo[5] = M[2][2];
-      // use the stored (symmetric) representation from here on so linearize and compute_error agree
-      M[1][0] = M[0][1]; M[2][0] = M[0][2]; M[2][1] = M[1][2];
-
-      const double ax = (double)px, ay = (double)py, az = (double)pz;
-      const double qx = ((T.R[0][0] * ax + T.R[0][1] * ay) + T.R[0][2] * az) + T.t[0];
-      const double qy = ((T.R[1][0] * ax + T.R[1][1] * ay) + T.R[1][2] * az) + T.t[1];
-      const double qz = ((T.R[2][0] * ax + T.R[2][1] * ay) + T.R[2][2] * az) + T.t[2];
-      const double e[3] = {(double)a.tgt_xyz[3 * (size_t)j] - qx, (double)a.tgt_xyz[3 * (size_t)j + 1] - qy,
-                           (double)a.tgt_xyz[3 * (size_t)j + 2] - qz};
-      double Me[3];
-#pragma unroll
-      for (int r = 0; r < 3; r++) Me[r] = (M[r][0] * e[0] + M[r][1] * e[1]) + M[r][2] * e[2];
-      v[27] = (e[0] * Me[0] + e[1] * Me[1]) + e[2] * Me[2];
-
-      // J = [S | -I], S = skew(q):  S = [[0,-qz,qy],[qz,0,-qx],[-qy,qx,0]]
-      const double S[3][3] = {{0.0, -qz, qy}, {qz, 0.0, -qx}, {-qy, qx, 0.0}};
-      double MS[3][3];  // M * S
-#pragma unroll
-      for (int r = 0; r < 3; r++)
-#pragma unroll
-        for (int c = 0; c < 3; c++) MS[r][c] = (M[r][0] * S[0][c] + M[r][1] * S[1][c]) + M[r][2] * S[2][c];
-      double H[6][6];
-#pragma unroll
-      for (int r = 0; r < 3; r++)
-#pragma unroll
-        for (int c = 0; c < 3; c++) {
-          H[r][c] = (S[0][r] * MS[0][c] + S[1][r] * MS[1][c]) + S[2][r] * MS[2][c];  // S^T M S
-          H[r][3 + c] = -((S[0][r] * M[0][c] + S[1][r] * M[1][c]) + S[2][r] * M[2][c]);  // -S^T M
-          H[3 + r][3 + c] = M[r][c];
-        }
-      int o = 0;
-#pragma unroll
-      for (int r = 0; r < 6; r++)
-#pragma unroll
-        for (int c = r; c < 6; c++) v[o++] = H[r][c];
-#pragma unroll
-      for (int r = 0; r < 3; r++) {
-        v[21 + r] = (S[0][r] * Me[0] + S[1][r] * Me[1]) + S[2][r] * Me[2];  // S^T M e
-        v[24 + r] = -Me[r];
-      }
-    }
+    if (j >= 0) linearize_point(T, i, j, a.src_xyz, a.src_cov, a.tgt_xyz, a.tgt_cov, a.mahal, v);
   }
   block_reduce_finalize<kRed>(v, a.partial, a.out, a.counter, a.host_out, a.host_seq, a.seq);
 }
@@ -453,22 +476,311 @@ error_kernel(PoseD T, ErrArgs a) {
   double v[1] = {0.0};
   if (i < a.end) {
     const int32_t j = a.corr[i];
-    if (j >= 0) {
-      const double ax = (double)a.src_xyz[3 * (size_t)i], ay = (double)a.src_xyz[3 * (size_t)i + 1],
-                   az = (double)a.src_xyz[3 * (size_t)i + 2];
-      const double qx = ((T.R[0][0] * ax + T.R[0][1] * ay) + T.R[0][2] * az) + T.t[0];
-      const double qy = ((T.R[1][0] * ax + T.R[1][1] * ay) + T.R[1][2] * az) + T.t[1];
-      const double qz = ((T.R[2][0] * ax + T.R[2][1] * ay) + T.R[2][2] * az) + T.t[2];
-      const double e[3] = {(double)a.tgt_xyz[3 * (size_t)j] - qx, (double)a.tgt_xyz[3 * (size_t)j + 1] - qy,
-                           (double)a.tgt_xyz[3 * (size_t)j + 2] - qz};
-      const double* m = a.mahal + 6 * (size_t)i;
-      const double Me0 = (m[0] * e[0] + m[1] * e[1]) + m[2] * e[2];
-      const double Me1 = (m[1] * e[0] + m[3] * e[1]) + m[4] * e[2];
-      const double Me2 = (m[2] * e[0] + m[4] * e[1]) + m[5] * e[2];
-      v[0] = (e[0] * Me0 + e[1] * Me1) + e[2] * Me2;
-    }
+    if (j >= 0) v[0] = error_point(T, i, j, a.src_xyz, a.tgt_xyz, a.mahal);
   }
   block_reduce_finalize<1>(v, a.partial, a.out, a.counter, a.host_out, a.host_seq, a.seq);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Device-resident Levenberg-Marquardt loop: ONE persistent kernel per align()
+// (lsq_registration_impl.hpp:53-78 computeTransformation + :125-173 step_lm, with fgi:242-378 as its phases).
+//
+//   outer iteration:  phase L  every warp: correspondence search (warp-cooperative exact 1-NN in the target grid) for 4
+//                              source points, then lanes 0..3 build Mahalanobis + J^T M J + J^T M e of their point in
+//                              fp64; per-thread 28-double accumulators -> block reduction -> partial[block][28]
+//                     grid barrier; every block sums the partials in the same fixed order (H, b, y0 identical everywhere)
+//                     and its thread 0 takes the LM decision redundantly — no broadcast, no host.
+//     up to 10 trials: solve (H + lambda I) d = -b (pivoted LDL^T), delta = (so3_exp, t), xi = delta x0
+//                     phase E  sum e^T M e at xi with frozen correspondences / cached Mahalanobis; grid barrier; rho test.
+// The host launches it once and spins on one sequence word in mapped pinned memory: zero host round trips inside the loop
+// (the host-driven path below costs one launch + one spin-wait per phase).  Sums are deterministic: fixed point -> lane,
+// fixed block order.
+// Launch shape: one 256-thread block per SM at most (half of each SM's registers), ordinary launch + an atomic-counter
+// grid barrier instead of a cooperative launch: the kernel starts on whatever SMs have room while the mapper's kernels
+// run on the other stream (a cooperative launch would wait for — and then occupy — the whole GPU).  All blocks are
+// co-resident once the other kernels drain (grid <= SM count), so the barrier cannot deadlock; a poll budget turns a
+// lost peer into an error status instead of a hang.
+// ------------------------------------------------------------------------------------------------
+constexpr int kLmBlock = 256;     // threads per block of align_lm_kernel
+constexpr int kLmChunk = 4;       // source points per warp visit
+constexpr int kLmSeg = 8;         // partial-sum segments per value in the cross-block reduction
+constexpr long long kLmPollBudget = 1ll << 27;  // barrier polls before giving up (seconds of wall time)
+
+struct LmResult {  // lives in mapped pinned host memory; written by block 0
+  double R[9], t[3];      // final pose x0
+  double H[36];           // Hessian of the last accepted step (lsq:169)
+  double lambda;
+  int iterations;         // outer iterations run (= value align() returns)
+  int converged;
+  int status;             // 0 ok, 1 "lm not converged" (step_lm returned false), 3 grid barrier timed out
+  int n_lin, n_err;
+  int pad;
+  unsigned long long seq;
+};
+
+struct LmArgs {
+  GridView tgt;
+  int begin, end;            // source range of this rank
+  double max_corr_sq;
+  const float* src_xyz;
+  const double* src_cov;
+  const float* tgt_xyz;
+  const double* tgt_cov;
+  int32_t* corr;
+  float* sqd;
+  double* mahal;
+  double* partL;             // [blocks][28]
+  double* partE;             // [2][blocks]
+  unsigned int* barrier;     // grid-barrier counter, zero at launch
+  int max_iterations, lm_max_iterations;
+  double rot_eps, trans_eps, init_lambda_factor;
+  Iso guess;
+  LmResult* result;          // device alias of the mapped host block
+  unsigned long long seq;
+};
+
+__device__ __forceinline__ PoseD make_pose_dev(const Iso& x) {
+  PoseD p;
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      p.R[i][j] = x.R[i][j];
+      p.Rf[i][j] = (float)x.R[i][j];
+    }
+    p.t[i] = x.t[i];
+    p.tf[i] = (float)x.t[i];
+  }
+  return p;
+}
+
+// fp32 transform of a source point in the order Eigen's packet product evaluates trans_f * getVector4fMap() (fgi:260)
+__device__ __forceinline__ void transform_f32(const PoseD& T, float px, float py, float pz, float& tx, float& ty, float& tz) {
+  tx = __fadd_rn(__fadd_rn(__fmul_rn(T.Rf[0][0], px), __fmul_rn(T.Rf[0][1], py)), __fadd_rn(__fmul_rn(T.Rf[0][2], pz), T.tf[0]));
+  ty = __fadd_rn(__fadd_rn(__fmul_rn(T.Rf[1][0], px), __fmul_rn(T.Rf[1][1], py)), __fadd_rn(__fmul_rn(T.Rf[1][2], pz), T.tf[1]));
+  tz = __fadd_rn(__fadd_rn(__fmul_rn(T.Rf[2][0], px), __fmul_rn(T.Rf[2][1], py)), __fadd_rn(__fmul_rn(T.Rf[2][2], pz), T.tf[2]));
+}
+
+// Grid barrier on a monotonically increasing counter (zeroed by the host before the launch): arrival k of every block
+// completes when the counter reaches k * gridDim.x.  Returns false when the poll budget ran out.
+__device__ __forceinline__ bool grid_barrier(unsigned int* counter, unsigned int& epoch) {
+  __shared__ int s_ok;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    epoch += gridDim.x;
+    __threadfence();  // release this block's global writes
+    atomicAdd(counter, 1u);
+    long long polls = 0;
+    int ok = 1;
+    while (true) {
+      unsigned int v;
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+      if (v >= epoch) break;
+      if (++polls > kLmPollBudget) {
+        ok = 0;
+        break;
+      }
+    }
+    s_ok = ok;
+  }
+  __syncthreads();
+  return s_ok != 0;
+}
+
+// Block-level sum of NV doubles per thread -> out[NV] (thread t < NV writes value t); warps in index order.
+template <int NV>
+__device__ __forceinline__ void block_sum_store(const double* v, double* __restrict__ out) {
+  __shared__ double s_red[kLmBlock / 32][NV];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < NV; k++) {
+    const double r = warp_sum_d(v[k]);
+    if (lane == 0) s_red[warp][k] = r;
+  }
+  __syncthreads();
+  if (threadIdx.x < NV) {
+    double r = 0.0;
+#pragma unroll
+    for (int w = 0; w < kLmBlock / 32; w++) r += s_red[w][threadIdx.x];
+    out[threadIdx.x] = r;
+  }
+  __syncthreads();
+}
+
+// Sum partial[b][NV] over the blocks in a fixed order, identically in every block: thread (seg, k) adds the blocks
+// b = seg, seg + kLmSeg, ...; thread k < NV then adds the kLmSeg segment sums in order.  Result in s_out[NV].
+template <int NV>
+__device__ __forceinline__ void reduce_partials(const double* __restrict__ partial, int nblocks, double* s_out) {
+  __shared__ double s_seg[kLmSeg][NV];
+  const int k = threadIdx.x % NV, seg = threadIdx.x / NV;
+  if (seg < kLmSeg) {
+    double r = 0.0;
+    for (int b = seg; b < nblocks; b += kLmSeg) r += __ldcg(partial + (size_t)b * NV + k);
+    s_seg[seg][k] = r;
+  }
+  __syncthreads();
+  if (threadIdx.x < NV) {
+    double r = 0.0;
+#pragma unroll
+    for (int sg = 0; sg < kLmSeg; sg++) r += s_seg[sg][threadIdx.x];
+    s_out[threadIdx.x] = r;
+  }
+  __syncthreads();
+}
+
+// (256, 2): caps the kernel at 128 registers so that one block takes half of an SM's register file
+__global__ void __launch_bounds__(kLmBlock, 2)
+align_lm_kernel(LmArgs a) {
+  __shared__ double s_sum[kRed];
+  __shared__ Iso s_x0, s_xi, s_delta;
+  __shared__ double s_H[6][6], s_b[6], s_d[6];
+  __shared__ double s_y0, s_lambda, s_nu;
+  __shared__ int s_state;  // 0: run another trial / phase, 1: step accepted or converged inside step_lm, 2: lm failed
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int warps_per_block = kLmBlock / 32;
+  const int gwarp = blockIdx.x * warps_per_block + warp, total_warps = gridDim.x * warps_per_block;
+  const int gthread = blockIdx.x * kLmBlock + threadIdx.x, total_threads = gridDim.x * kLmBlock;
+  const int n = a.end - a.begin;
+  const int nchunks = (n + kLmChunk - 1) / kLmChunk;
+
+  if (threadIdx.x == 0) {
+    s_x0 = a.guess;
+    s_lambda = -1.0;
+  }
+  __syncthreads();
+
+  unsigned int epoch = 0;  // thread 0's barrier target
+  int iterations = 0, converged = 0, status = 0, n_lin = 0, n_err = 0;
+  for (int it = 0; it < a.max_iterations && !converged; it++) {
+    iterations = it + 1;
+    // ---------------- phase L: correspondences + linearisation at x0 ----------------
+    {
+      const PoseD T = make_pose_dev(s_x0);
+      double v[kRed];
+#pragma unroll
+      for (int k = 0; k < kRed; k++) v[k] = 0.0;
+      for (int c = gwarp; c < nchunks; c += total_warps) {
+        int my_i = -1, my_j = -1;
+#pragma unroll
+        for (int k = 0; k < kLmChunk; k++) {
+          const int i = a.begin + c * kLmChunk + k;
+          if (i < a.end) {  // warp-uniform
+            const float px = a.src_xyz[3 * (size_t)i], py = a.src_xyz[3 * (size_t)i + 1], pz = a.src_xyz[3 * (size_t)i + 2];
+            float tx, ty, tz, d2;
+            uint32_t id;
+            transform_f32(T, px, py, pz, tx, ty, tz);
+            grid_nn_warp(a.tgt, tx, ty, tz, d2, id);
+            const int32_t j = ((a.tgt.n > 0) && ((double)d2 < a.max_corr_sq)) ? (int32_t)id : -1;
+            if (lane == 0) {
+              a.sqd[i] = d2;
+              a.corr[i] = j;
+            }
+            if (lane == k) {
+              my_i = i;
+              my_j = j;
+            }
+          }
+        }
+        if (my_j >= 0) linearize_point(T, my_i, my_j, a.src_xyz, a.src_cov, a.tgt_xyz, a.tgt_cov, a.mahal, v);
+      }
+      block_sum_store<kRed>(v, a.partL + (size_t)blockIdx.x * kRed);
+    }
+    if (!grid_barrier(a.barrier, epoch)) {
+      status = 3;
+      break;
+    }
+    reduce_partials<kRed>(a.partL, gridDim.x, s_sum);
+    n_lin++;
+    if (threadIdx.x == 0) {
+      int o = 0;
+      for (int r = 0; r < 6; r++)
+        for (int c = r; c < 6; c++) {
+          s_H[r][c] = s_sum[o];
+          s_H[c][r] = s_sum[o];
+          o++;
+        }
+      for (int r = 0; r < 6; r++) s_b[r] = s_sum[21 + r];
+      s_y0 = s_sum[27];
+      if (s_lambda < 0.0) {  // lsq:130-132
+        double mx = 0.0;
+        for (int i = 0; i < 6; i++) mx = fmax(mx, fabs(s_H[i][i]));
+        s_lambda = a.init_lambda_factor * mx;
+      }
+      s_nu = 2.0;
+      s_state = 0;
+    }
+    __syncthreads();
+    // ---------------- LM trials (lsq:135-170) ----------------
+    int trial = 0;
+    for (; trial < a.lm_max_iterations; trial++) {
+      if (threadIdx.x == 0) lm_trial(s_H, s_b, s_lambda, s_x0, s_d, s_delta, s_xi);
+      __syncthreads();
+      // phase E: error at xi with frozen correspondences
+      {
+        const PoseD T = make_pose_dev(s_xi);
+        double v[1] = {0.0};
+        for (int i = a.begin + gthread; i < a.end; i += total_threads) {
+          const int32_t j = __ldcg(a.corr + i);  // written by another block in phase L: through L2
+          if (j >= 0) v[0] += error_point(T, i, j, a.src_xyz, a.tgt_xyz, a.mahal);
+        }
+        block_sum_store<1>(v, a.partE + (size_t)(trial & 1) * gridDim.x + blockIdx.x);
+      }
+      if (!grid_barrier(a.barrier, epoch)) {
+        status = 3;
+        break;
+      }
+      __shared__ double s_yi[1];
+      reduce_partials<1>(a.partE + (size_t)(trial & 1) * gridDim.x, gridDim.x, s_yi);
+      n_err++;
+      if (threadIdx.x == 0) {
+        const double yi = s_yi[0];
+        double dot = 0.0;
+        for (int i = 0; i < 6; i++) dot += s_d[i] * (s_lambda * s_d[i] - s_b[i]);
+        const double rho = (s_y0 - yi) / dot;
+        if (rho < 0) {
+          if (lm_is_converged(a.rot_eps, a.trans_eps, s_delta)) {
+            s_state = 1;  // step_lm returns true without moving x0
+          } else {
+            s_lambda = s_nu * s_lambda;
+            s_nu = 2 * s_nu;
+            s_state = 0;
+          }
+        } else {
+          s_x0 = s_xi;
+          s_lambda = s_lambda * fmax(1.0 / 3.0, 1 - pow(2 * rho - 1, 3));
+          if (blockIdx.x == 0)
+            for (int r = 0; r < 6; r++)
+              for (int c = 0; c < 6; c++) a.result->H[6 * r + c] = s_H[r][c];
+          s_state = 1;
+        }
+      }
+      __syncthreads();
+      if (s_state == 1) break;
+    }
+    if (status == 3) break;
+    if (s_state != 1) {  // the 10 trials were rejected: "lm not converged!!" (lsq:70-73)
+      status = 1;
+      break;
+    }
+    converged = lm_is_converged(a.rot_eps, a.trans_eps, s_delta) ? 1 : 0;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    LmResult* r = a.result;
+    for (int i = 0; i < 3; i++) {
+      for (int j = 0; j < 3; j++) r->R[3 * i + j] = s_x0.R[i][j];
+      r->t[i] = s_x0.t[i];
+    }
+    r->lambda = s_lambda;
+    r->iterations = iterations;
+    r->converged = converged;
+    r->status = status;
+    r->n_lin = n_lin;
+    r->n_err = n_err;
+    __threadfence_system();
+    *(volatile unsigned long long*)&r->seq = a.seq;
+    __threadfence_system();
+  }
 }
 
 __global__ void f64_to_f32_kernel(size_t n, const double* __restrict__ in, float* __restrict__ out) {
@@ -484,94 +796,6 @@ __global__ void identity_filter_kernel(int n, int32_t* f) {
 // ------------------------------------------------------------------------------------------------
 // host side: 6x6 LDLT, SE(3) helpers
 // ------------------------------------------------------------------------------------------------
-// Pivoted LDL^T of a symmetric 6x6 and solve, following Eigen's LDLT (Eigen/src/Cholesky/LDLT.h:
-// unblocked lower factorisation with diagonal pivoting, then P^T L^-T D^-1 L^-1 P b).
-static void ldlt_solve6(const double Hin[6][6], const double rhs[6], double x[6]) {
-  const int n = 6;
-  double A[6][6];
-  int tr[6];
-  for (int i = 0; i < n; i++)
-    for (int j = 0; j < n; j++) A[i][j] = Hin[i][j];
-  for (int k = 0; k < n; k++) {
-    int piv = k;
-    double big = std::fabs(A[k][k]);
-    for (int i = k + 1; i < n; i++)
-      if (std::fabs(A[i][i]) > big) {
-        big = std::fabs(A[i][i]);
-        piv = i;
-      }
-    tr[k] = piv;
-    if (piv != k) {  // symmetric row/column interchange on the lower triangle
-      const int s = n - piv - 1;
-      for (int c = 0; c < k; c++) std::swap(A[k][c], A[piv][c]);
-      for (int r = 0; r < s; r++) std::swap(A[piv + 1 + r][k], A[piv + 1 + r][piv]);
-      std::swap(A[k][k], A[piv][piv]);
-      for (int i = k + 1; i < piv; i++) std::swap(A[i][k], A[piv][i]);
-    }
-    const int rs = n - k - 1;
-    if (k > 0) {
-      double temp[6];
-      for (int c = 0; c < k; c++) temp[c] = A[c][c] * A[k][c];
-      double acc = 0.0;
-      for (int c = 0; c < k; c++) acc += A[k][c] * temp[c];
-      A[k][k] -= acc;
-      for (int r = 0; r < rs; r++) {
-        double a2 = 0.0;
-        for (int c = 0; c < k; c++) a2 += A[k + 1 + r][c] * temp[c];
-        A[k + 1 + r][k] -= a2;
-      }
-    }
-    const double akk = A[k][k];
-    const bool valid = std::fabs(akk) > 0.0;
-    if (k == 0 && !valid) {
-      for (int j = 0; j < n; j++) tr[j] = j;
-      break;
-    }
-    if (rs > 0 && valid)
-      for (int r = 0; r < rs; r++) A[k + 1 + r][k] /= akk;
-  }
-  double y[6];
-  for (int i = 0; i < n; i++) y[i] = rhs[i];
-  for (int k = 0; k < n; k++) std::swap(y[k], y[tr[k]]);          // P b
-  for (int i = 0; i < n; i++)                                      // L^-1
-    for (int c = 0; c < i; c++) y[i] -= A[i][c] * y[c];
-  const double tol = 1.0 / std::numeric_limits<double>::max();
-  for (int i = 0; i < n; i++) y[i] = (std::fabs(A[i][i]) > tol) ? y[i] / A[i][i] : 0.0;  // D^-1
-  for (int i = n - 1; i >= 0; i--)                                 // L^-T
-    for (int c = i + 1; c < n; c++) y[i] -= A[c][i] * y[c];
-  for (int k = n - 1; k >= 0; k--) std::swap(y[k], y[tr[k]]);      // P^T
-  for (int i = 0; i < n; i++) x[i] = y[i];
-}
-
-struct Iso {  // rigid transform, double
-  double R[3][3], t[3];
-};
-
-static void so3_exp_matrix(const double w[3], double R[3][3]) {  // FG/include/fast_gicp/so3/so3.hpp:58-77
-  const double theta_sq = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
-  double imag, real;
-  if (theta_sq < 1e-10) {
-    const double theta_quad = theta_sq * theta_sq;
-    imag = 0.5 - 1.0 / 48.0 * theta_sq + 1.0 / 3840.0 * theta_quad;
-    real = 1.0 - 1.0 / 8.0 * theta_sq + 1.0 / 384.0 * theta_quad;
-  } else {
-    const double theta = std::sqrt(theta_sq);
-    const double half = 0.5 * theta;
-    imag = std::sin(half) / theta;
-    real = std::cos(half);
-  }
-  quat_to_matrix(imag * w[0], imag * w[1], imag * w[2], real, R);
-}
-
-static Iso iso_mul(const Iso& a, const Iso& b) {  // a * b
-  Iso r;
-  for (int i = 0; i < 3; i++) {
-    for (int j = 0; j < 3; j++) r.R[i][j] = (a.R[i][0] * b.R[0][j] + a.R[i][1] * b.R[1][j]) + a.R[i][2] * b.R[2][j];
-    r.t[i] = ((a.R[i][0] * b.t[0] + a.R[i][1] * b.t[1]) + a.R[i][2] * b.t[2]) + a.t[i];
-  }
-  return r;
-}
-
 static PoseD make_pose(const Iso& x) {
   PoseD p;
   for (int i = 0; i < 3; i++) {
@@ -631,6 +855,11 @@ struct gsicp_gicp {
   int shard_count = 1, shard_index = 0;
   gsicp_allreduce_fn reduce = nullptr;
   void* reduce_user = nullptr;
+  bool host_lm = false;          // GSICP_HOST_LM=1: host-driven LM loop (one launch + one spin-wait per phase)
+  Scratch lm_partL, lm_partE, lm_barrier;
+  LmResult* h_lm = nullptr;      // mapped pinned result block of align_lm_kernel
+  LmResult* d_lm = nullptr;
+  int lm_max_blocks = 0;         // co-resident blocks of align_lm_kernel on this device
   bool timing = false;
   double t_cov = 0, t_lin = 0, t_err = 0;
   int n_lin = 0, n_err = 0;
@@ -1061,14 +1290,7 @@ int run_error(gsicp_gicp* h, const Iso& x, double* err) {  // fgi:355-378
   return GSICP_OK;
 }
 
-bool is_converged(const gsicp_gicp* h, const Iso& delta) {  // lsq:81-90
-  double m = 0.0;
-  for (int i = 0; i < 3; i++)
-    for (int j = 0; j < 3; j++) m = std::max(m, (1.0 / h->rot_eps) * std::fabs(delta.R[i][j] - (i == j ? 1.0 : 0.0)));
-  double mt = 0.0;
-  for (int i = 0; i < 3; i++) mt = std::max(mt, (1.0 / h->trans_eps) * std::fabs(delta.t[i]));
-  return std::max(m, mt) < 1;
-}
+bool is_converged(const gsicp_gicp* h, const Iso& delta) { return lm_is_converged(h->rot_eps, h->trans_eps, delta); }
 
 // lsq:125-173.  Returns 1 = step taken / converged, 0 = failed ("lm not converged"), <0 = error.
 int step_lm(gsicp_gicp* h, Iso& x0, Iso& delta) {
@@ -1081,17 +1303,9 @@ int step_lm(gsicp_gicp* h, Iso& x0, Iso& delta) {
   }
   double nu = 2.0;
   for (int it = 0; it < h->lm_max_iterations; it++) {
-    double A[6][6], nb[6], d[6];
-    for (int i = 0; i < 6; i++) {
-      for (int j = 0; j < 6; j++) A[i][j] = H[i][j] + (i == j ? h->lm_lambda : 0.0);
-      nb[i] = -b[i];
-    }
-    ldlt_solve6(A, nb, d);
-    for (int i = 0; i < 3; i++)
-      for (int j = 0; j < 3; j++) delta.R[i][j] = (i == j);
-    so3_exp_matrix(d, delta.R);
-    delta.t[0] = d[3]; delta.t[1] = d[4]; delta.t[2] = d[5];
-    const Iso xi = iso_mul(delta, x0);
+    double d[6];
+    Iso xi;
+    lm_trial(H, b, h->lm_lambda, x0, d, delta, xi);
     double yi;
     if (int e = run_error(h, xi, &yi)) return e;
     double dot = 0.0;
@@ -1110,6 +1324,99 @@ int step_lm(gsicp_gicp* h, Iso& x0, Iso& delta) {
     return 1;
   }
   return 0;
+}
+
+// The whole LM loop of one align() on the device (align_lm_kernel): one launch, one spin-wait.
+// Returns the number of outer iterations (>= 1) or a negative error.
+int run_align_device(gsicp_gicp* h, Iso& x0) {
+  if (int e = ensure_lin_buffers(h)) return e;
+  if (h->corr_n != h->src.n) {
+    GSICP_CUDA(cudaMemsetAsync(h->corr.ptr, 0xff, (size_t)(h->src.n + 1) * 4, h->stream));
+    GSICP_CUDA(cudaMemsetAsync(h->sqd.ptr, 0, (size_t)(h->src.n + 1) * 4, h->stream));
+    h->corr_n = h->src.n;
+  }
+  if (!h->h_lm) {
+    GSICP_CUDA(cudaHostAlloc((void**)&h->h_lm, sizeof(LmResult), cudaHostAllocMapped));
+    std::memset(h->h_lm, 0, sizeof(LmResult));
+    GSICP_CUDA(cudaHostGetDevicePointer((void**)&h->d_lm, h->h_lm, 0));
+  }
+  if (h->lm_max_blocks == 0) {
+    int dev = 0, sms = 0;
+    GSICP_CUDA(cudaGetDevice(&dev));
+    GSICP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    h->lm_max_blocks = sms > 0 ? sms : 1;  // one block per SM: always co-resident on an otherwise idle device
+  }
+  int begin, end;
+  shard_range(h, h->src.n, begin, end);
+  const int nchunks = (end - begin + kLmChunk - 1) / kLmChunk;
+  int blocks = (nchunks + (kLmBlock / 32) - 1) / (kLmBlock / 32);
+  blocks = std::max(1, std::min(blocks, h->lm_max_blocks));
+  if (int e = h->lm_partL.ensure((size_t)h->lm_max_blocks * kRed * sizeof(double))) return e;
+  if (int e = h->lm_partE.ensure((size_t)h->lm_max_blocks * 2 * sizeof(double))) return e;
+  if (int e = h->lm_barrier.ensure(sizeof(unsigned int))) return e;
+  GSICP_CUDA(cudaMemsetAsync(h->lm_barrier.ptr, 0, sizeof(unsigned int), h->stream));
+  if (end > begin)
+    if (int e = ensure_grid(h, h->tgt)) return e;
+  LmArgs a;
+  a.tgt = h->tgt.grid.view();
+  a.begin = begin; a.end = end;
+  a.max_corr_sq = h->max_corr * h->max_corr;
+  a.src_xyz = h->src.xyz.as<float>(); a.src_cov = h->src.cov.as<double>();
+  a.tgt_xyz = h->tgt.xyz.as<float>(); a.tgt_cov = h->tgt.cov.as<double>();
+  a.corr = h->corr.as<int32_t>(); a.sqd = h->sqd.as<float>(); a.mahal = h->mahal.as<double>();
+  a.partL = h->lm_partL.as<double>(); a.partE = h->lm_partE.as<double>();
+  a.barrier = h->lm_barrier.as<unsigned int>();
+  a.max_iterations = h->max_iterations; a.lm_max_iterations = h->lm_max_iterations;
+  a.rot_eps = h->rot_eps; a.trans_eps = h->trans_eps; a.init_lambda_factor = h->lm_init_lambda_factor;
+  a.guess = x0;
+  a.result = h->d_lm;
+  a.seq = ++h->seq;
+  {
+    ProfScope ps(kProfLinearize, h->stream);  // slot "gicp_linearize": the whole device-resident LM loop
+    GSICP_LAUNCH(align_lm_kernel, blocks, kLmBlock, 0, h->stream, a);
+  }
+  GSICP_CUDA(cudaGetLastError());
+  // spin on the sequence word the kernel publishes into mapped pinned memory
+  volatile unsigned long long* p = &h->h_lm->seq;
+  long spins = 0;
+  while (*p != a.seq) {
+#if defined(__x86_64__)
+    __builtin_ia32_pause();
+#endif
+    if ((++spins & 0xfffff) == 0) {
+      const cudaError_t q = cudaStreamQuery(h->stream);
+      if (q != cudaSuccess && q != cudaErrorNotReady) {
+        set_error("align kernel failed: %s", cudaGetErrorString(q));
+        return GSICP_ECUDA;
+      }
+      if (q == cudaSuccess && *p != a.seq) {
+        set_error("align result was not published");
+        return GSICP_ECUDA;
+      }
+    }
+  }
+  const LmResult r = *h->h_lm;
+  for (int i = 0; i < 3; i++) {
+    for (int j = 0; j < 3; j++) x0.R[i][j] = r.R[3 * i + j];
+    x0.t[i] = r.t[i];
+  }
+  h->lm_lambda = r.lambda;
+  h->converged = r.converged != 0;
+  h->nr_iterations = r.iterations - 1;
+  h->n_lin = r.n_lin;
+  h->n_err = r.n_err;
+  // final_hessian_ is only assigned by an accepted step (lsq:169); it keeps its previous value otherwise
+  if (r.n_err > 0) {
+    bool any = false;
+    for (int i = 0; i < 36; i++) any = any || (r.H[i] != 0.0);
+    if (any) std::memcpy(h->final_hessian, r.H, sizeof(double) * 36);
+  }
+  if (r.status == 1) fprintf(stderr, "lm not converged!!\n");
+  if (r.status == 3) {
+    set_error("align: the device-side grid barrier timed out");
+    return GSICP_ECUDA;
+  }
+  return r.iterations;
 }
 
 int copy_out(gsicp_gicp* h, const Scratch& s, size_t bytes, void* out) {
@@ -1142,6 +1449,8 @@ gsicp_gicp* gsicp_gicp_create(void) {
   for (int i = 0; i < 36; i++) h->final_hessian[i] = (i % 7 == 0) ? 1.0 : 0.0;
   const char* t = std::getenv("GSICP_TIMING");
   h->timing = t && t[0] == '1';
+  const char* hl = std::getenv("GSICP_HOST_LM");
+  h->host_lm = hl && hl[0] == '1';
   if (cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess) {
     set_error("gsicp_gicp_create: no usable CUDA device (%s)", cudaGetErrorString(cudaGetLastError()));
     delete h;
@@ -1157,11 +1466,13 @@ void gsicp_gicp_destroy(gsicp_gicp* h) {
     s.ptr = nullptr;
   };
   for (Cloud* c : {&h->src, &h->tgt}) {
-    fr(c->xyz); fr(c->xyz_alt); fr(c->cov); fr(c->rots); fr(c->scales); fr(c->filter);
+    fr(c->xyz); fr(c->xyz_alt); fr(c->cov); fr(c->rots); fr(c->scales); fr(c->filter); fr(c->zvals);
     fr(c->grid.meta_buf); fr(c->grid.bbox_buf); fr(c->grid.cell_start); fr(c->grid.cursor); fr(c->grid.cell_of_pt);
     fr(c->grid.pts); fr(c->grid.cub_tmp);
   }
   fr(h->corr); fr(h->sqd); fr(h->mahal); fr(h->partial); fr(h->red_out); fr(h->counter); fr(h->staging_dev); fr(h->nn_id); fr(h->nn_d2);
+  fr(h->lm_partL); fr(h->lm_partE); fr(h->lm_barrier);
+  if (h->h_lm) cudaFreeHost(h->h_lm);
   if (h->h_red) cudaFreeHost(h->h_red);
   if (h->h_map) cudaFreeHost(h->h_map);
   if (h->h_stage) cudaFreeHost(h->h_stage);
@@ -1178,6 +1489,7 @@ int gsicp_gicp_set_max_knn_distance(gsicp_gicp* h, double d) { H_CHECK(h); h->kn
 int gsicp_gicp_set_correspondence_randomness(gsicp_gicp* h, int k) { H_CHECK(h); h->k = k; return GSICP_OK; }
 int gsicp_gicp_set_max_iterations(gsicp_gicp* h, int n) { H_CHECK(h); h->max_iterations = n; return GSICP_OK; }
 int gsicp_gicp_set_stream(gsicp_gicp* h, void* s) { H_CHECK(h); h->stream = (cudaStream_t)s; return GSICP_OK; }
+int gsicp_gicp_set_host_lm(gsicp_gicp* h, int on) { H_CHECK(h); h->host_lm = on != 0; return GSICP_OK; }
 
 int gsicp_gicp_set_input_source(gsicp_gicp* h, const void* xyz, int n, int is_f32) {
   H_CHECK(h);
@@ -1264,17 +1576,24 @@ int gsicp_gicp_align(gsicp_gicp* h, const float guess[16], float out[16]) {
   }
   h->lm_lambda = -1.0;
   int iters = 0;
-  for (int i = 0; i < h->max_iterations && !h->converged; i++) {
-    h->nr_iterations = i;
-    iters = i + 1;
-    Iso delta;
-    const int rc = step_lm(h, x0, delta);
-    if (rc < 0) return rc;
-    if (rc == 0) {
-      fprintf(stderr, "lm not converged!!\n");
-      break;
+  if (!h->host_lm && !h->timing && h->shard_count <= 1) {
+    // device-resident LM loop: one persistent kernel, zero host round trips inside the loop
+    if (h->d_lm) std::memset(h->h_lm->H, 0, sizeof(h->h_lm->H));
+    iters = run_align_device(h, x0);
+    if (iters < 0) return iters;
+  } else {
+    for (int i = 0; i < h->max_iterations && !h->converged; i++) {
+      h->nr_iterations = i;
+      iters = i + 1;
+      Iso delta;
+      const int rc = step_lm(h, x0, delta);
+      if (rc < 0) return rc;
+      if (rc == 0) {
+        fprintf(stderr, "lm not converged!!\n");
+        break;
+      }
+      h->converged = is_converged(h, delta);
     }
-    h->converged = is_converged(h, delta);
   }
   for (int i = 0; i < 3; i++) {
     for (int j = 0; j < 3; j++) h->final_transformation[4 * i + j] = (float)x0.R[i][j];

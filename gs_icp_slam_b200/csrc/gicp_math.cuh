@@ -206,4 +206,124 @@ GM_HD bool inverse3(const double a[3][3], double inv[3][3]) {
   return true;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Levenberg-Marquardt step algebra of LsqRegistration (lsq_registration_impl.hpp:81-90, 125-173), shared by the host
+// loop and the device-resident loop (align_lm_kernel): rigid transforms, so3_exp, pivoted 6x6 LDL^T.
+// ---------------------------------------------------------------------------------------------------------------
+struct Iso {  // rigid transform, double
+  double R[3][3], t[3];
+};
+
+GM_HD Iso iso_mul(const Iso& a, const Iso& b) {  // a * b
+  Iso r;
+  for (int i = 0; i < 3; i++) {
+    for (int j = 0; j < 3; j++) r.R[i][j] = (a.R[i][0] * b.R[0][j] + a.R[i][1] * b.R[1][j]) + a.R[i][2] * b.R[2][j];
+    r.t[i] = ((a.R[i][0] * b.t[0] + a.R[i][1] * b.t[1]) + a.R[i][2] * b.t[2]) + a.t[i];
+  }
+  return r;
+}
+
+GM_HD void so3_exp_matrix(const double w[3], double R[3][3]) {  // FG/include/fast_gicp/so3/so3.hpp:58-77
+  const double theta_sq = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
+  double imag, real;
+  if (theta_sq < 1e-10) {
+    const double theta_quad = theta_sq * theta_sq;
+    imag = 0.5 - 1.0 / 48.0 * theta_sq + 1.0 / 3840.0 * theta_quad;
+    real = 1.0 - 1.0 / 8.0 * theta_sq + 1.0 / 384.0 * theta_quad;
+  } else {
+    const double theta = sqrt(theta_sq);
+    const double half = 0.5 * theta;
+    imag = sin(half) / theta;
+    real = cos(half);
+  }
+  quat_to_matrix(imag * w[0], imag * w[1], imag * w[2], real, R);
+}
+
+GM_HD void gm_swap(double& a, double& b) {
+  const double t = a;
+  a = b;
+  b = t;
+}
+
+// Pivoted LDL^T of a symmetric 6x6 and solve, following Eigen's LDLT (Eigen/src/Cholesky/LDLT.h:
+// unblocked lower factorisation with diagonal pivoting, then P^T L^-T D^-1 L^-1 P b).
+GM_HD void ldlt_solve6(const double Hin[6][6], const double rhs[6], double x[6]) {
+  const int n = 6;
+  double A[6][6];
+  int tr[6];
+  for (int i = 0; i < n; i++)
+    for (int j = 0; j < n; j++) A[i][j] = Hin[i][j];
+  for (int k = 0; k < n; k++) {
+    int piv = k;
+    double big = fabs(A[k][k]);
+    for (int i = k + 1; i < n; i++)
+      if (fabs(A[i][i]) > big) {
+        big = fabs(A[i][i]);
+        piv = i;
+      }
+    tr[k] = piv;
+    if (piv != k) {  // symmetric row/column interchange on the lower triangle
+      const int s = n - piv - 1;
+      for (int c = 0; c < k; c++) gm_swap(A[k][c], A[piv][c]);
+      for (int r = 0; r < s; r++) gm_swap(A[piv + 1 + r][k], A[piv + 1 + r][piv]);
+      gm_swap(A[k][k], A[piv][piv]);
+      for (int i = k + 1; i < piv; i++) gm_swap(A[i][k], A[piv][i]);
+    }
+    const int rs = n - k - 1;
+    if (k > 0) {
+      double temp[6];
+      for (int c = 0; c < k; c++) temp[c] = A[c][c] * A[k][c];
+      double acc = 0.0;
+      for (int c = 0; c < k; c++) acc += A[k][c] * temp[c];
+      A[k][k] -= acc;
+      for (int r = 0; r < rs; r++) {
+        double a2 = 0.0;
+        for (int c = 0; c < k; c++) a2 += A[k + 1 + r][c] * temp[c];
+        A[k + 1 + r][k] -= a2;
+      }
+    }
+    const double akk = A[k][k];
+    const bool valid = fabs(akk) > 0.0;
+    if (k == 0 && !valid) {
+      for (int j = 0; j < n; j++) tr[j] = j;
+      break;
+    }
+    if (rs > 0 && valid)
+      for (int r = 0; r < rs; r++) A[k + 1 + r][k] /= akk;
+  }
+  double y[6];
+  for (int i = 0; i < n; i++) y[i] = rhs[i];
+  for (int k = 0; k < n; k++) gm_swap(y[k], y[tr[k]]);           // P b
+  for (int i = 0; i < n; i++)                                      // L^-1
+    for (int c = 0; c < i; c++) y[i] -= A[i][c] * y[c];
+  const double tol = 1.0 / DBL_MAX;
+  for (int i = 0; i < n; i++) y[i] = (fabs(A[i][i]) > tol) ? y[i] / A[i][i] : 0.0;  // D^-1
+  for (int i = n - 1; i >= 0; i--)                                 // L^-T
+    for (int c = i + 1; c < n; c++) y[i] -= A[c][i] * y[c];
+  for (int k = n - 1; k >= 0; k--) gm_swap(y[k], y[tr[k]]);      // P^T
+  for (int i = 0; i < n; i++) x[i] = y[i];
+}
+
+GM_HD bool lm_is_converged(double rot_eps, double trans_eps, const Iso& delta) {  // lsq:81-90
+  double m = 0.0;
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) m = fmax(m, (1.0 / rot_eps) * fabs(delta.R[i][j] - (i == j ? 1.0 : 0.0)));
+  double mt = 0.0;
+  for (int i = 0; i < 3; i++) mt = fmax(mt, (1.0 / trans_eps) * fabs(delta.t[i]));
+  return fmax(m, mt) < 1;
+}
+
+// One trial of step_lm (lsq:137-146): solve (H + lambda I) d = -b, delta = (so3_exp(d[0:3]), d[3:6]), xi = delta * x0.
+GM_HD void lm_trial(const double H[6][6], const double b[6], double lambda, const Iso& x0, double d[6], Iso& delta, Iso& xi) {
+  double A[6][6], nb[6];
+  for (int i = 0; i < 6; i++) {
+    for (int j = 0; j < 6; j++) A[i][j] = H[i][j] + (i == j ? lambda : 0.0);
+    nb[i] = -b[i];
+  }
+  ldlt_solve6(A, nb, d);
+  so3_exp_matrix(d, delta.R);
+  delta.t[0] = d[3]; delta.t[1] = d[4]; delta.t[2] = d[5];
+  xi = iso_mul(delta, x0);
+}
+
 }  // namespace gsicp

@@ -231,6 +231,10 @@ class FastGICP:
     def set_stream(self, cuda_stream):
         check(lib.gsicp_gicp_set_stream(self._h, int(cuda_stream)))
 
+    def set_host_lm(self, on):
+        """Test / A-B hook: drive the LM loop from the host instead of the device-resident kernel (same results)."""
+        check(lib.gsicp_gicp_set_host_lm(self._h, int(bool(on))))
+
     def set_shard(self, count, index, reduce_cb=None):
         """Shard the source points over `count` ranks; reduce_cb(device_ptr, count, stream) all-reduces in place."""
         if reduce_cb is None:

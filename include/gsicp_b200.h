@@ -226,6 +226,9 @@ int gsicp_gicp_set_shard(gsicp_gicp*, int shard_count, int shard_index,
 
 /* Stream on which the handle's kernels run (default: legacy default stream 0). */
 int gsicp_gicp_set_stream(gsicp_gicp*, void* stream);
+/* Test / A-B hook: 1 = drive the LM loop from the host (one launch + one wait per linearize / compute_error), 0 (default) =
+ * the device-resident loop (one persistent kernel per align, lsq_registration_impl.hpp:53-173 on the GPU).  Same results. */
+int gsicp_gicp_set_host_lm(gsicp_gicp* h, int on);
 /* Timing of the last align(): milliseconds spent in each stage, measured with CUDA events on the
  * handle's stream: [0]=source covariance, [1]=linearize total, [2]=compute_error total,
  * [3]=number of linearize launches, [4]=number of compute_error launches. */

@@ -241,3 +241,55 @@ def test_dist2_matches_bruteforce_and_reference(cuda):
         a, b = distCUDA2(big), ref_cuda.ref_dist2(big)
         assert torch.allclose(a, b, rtol=2e-5, atol=1e-12)
     assert torch.isinf(distCUDA2(torch.zeros((2, 3), device=cuda))).all()  # fewer than 3 neighbours -> inf, like FLT_MAX sums
+
+
+def test_device_lm_loop_matches_host_driven_loop(cuda):
+    """align() runs the whole LM loop in one persistent kernel (align_lm_kernel); the host-driven loop (one launch + one
+    wait per linearize / compute_error) is kept as the A-B reference: same iteration counts, poses to 1e-12, identical
+    correspondences, final Hessian to 1e-12 relative — on C1 and on the tracker sequence shape."""
+    import pygicp
+
+    tgt, src, T = S.gicp_pair(10000, 10000)
+    out = []
+    for host in (False, True):
+        r = pygicp.FastGICP()
+        r.set_host_lm(host)
+        r.set_max_correspondence_distance(0.05)
+        r.set_max_knn_distance(99999)
+        r.set_input_target(tgt)
+        r.calculate_target_covariance_with_filter()
+        res = []
+        for guess in (np.eye(4), np.array(T) + 1e-3):
+            r.set_input_source(src)
+            p = r.align(guess.astype(np.float32))
+            c, d = r.get_source_correspondence()
+            res.append((p, r.last_iterations, r.has_converged(), c, d, r.get_final_hessian()))
+        out.append(res)
+    for a, b in zip(*out):
+        assert a[1] == b[1] and a[2] == b[2]
+        assert np.abs(a[0].astype(np.float64) - b[0]).max() <= 1e-12
+        assert np.array_equal(a[3], b[3]) and np.array_equal(a[4], b[4])
+        assert np.abs(a[5] - b[5]).max() <= 1e-12 * np.abs(b[5]).max()
+
+
+def test_device_lm_loop_rejected_steps_and_iteration_cap(cuda):
+    """A poor initial guess exercises rejected LM trials (lambda growth) and a capped iteration count, on both loops."""
+    import pygicp
+
+    tgt, src, T = S.gicp_pair(6000, 5000, 30, 31)
+    bad = np.array(T)
+    bad[:3, 3] += [0.12, -0.1, 0.08]
+    out = []
+    for host in (False, True):
+        r = pygicp.FastGICP()
+        r.set_host_lm(host)
+        r.set_max_correspondence_distance(0.3)
+        r.set_max_knn_distance(99999)
+        r.set_max_iterations(7)
+        r.set_input_target(tgt)
+        r.calculate_target_covariance()
+        r.set_input_source(src)
+        p = r.align(bad.astype(np.float32))
+        out.append((p, r.last_iterations, r.has_converged()))
+    assert out[0][1] == out[1][1] and out[0][2] == out[1][2]
+    assert np.abs(out[0][0].astype(np.float64) - out[1][0]).max() <= 1e-10
