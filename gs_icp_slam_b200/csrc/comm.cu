@@ -1,0 +1,104 @@
+// comm.cu — host side of the multi-GPU exchange layer (comm.cuh): segment allocation, CUDA IPC mapping of the peers'
+// segments, stream-ordered barrier.  One process per GPU; the 64-byte IPC handles travel over whatever channel the
+// application has (torch.distributed.all_gather_object in gs_icp_slam_b200/sharding.py).
+#include <cstring>
+#include "comm.cuh"
+#include "host_common.h"
+
+namespace gsicp {
+
+// One warp: lane r signals rank r (release: everything enqueued before on this stream is visible), then waits for
+// rank r's signal.  Sequence numbers are monotone, so a fast peer's later signal also satisfies the wait.
+__global__ void comm_barrier_kernel(CommView c, unsigned long long seq, int* status) {
+  const int r = threadIdx.x;
+  if (r < c.world) {
+    __threadfence_system();
+    unsigned long long* f = reinterpret_cast<unsigned long long*>(c.seg[r] + kCommBarOff) + c.rank;
+    st_release_sys(f, seq);
+    const unsigned long long* mine = reinterpret_cast<const unsigned long long*>(c.seg[c.rank] + kCommBarOff) + r;
+    long long polls = 0;
+    while (ld_acquire_sys(mine) < seq) {
+      if (++polls > kCommPollBudget) {
+        if (status) *status = 1;
+        break;
+      }
+    }
+    __threadfence_system();
+  }
+}
+
+int comm_stream_barrier(gsicp_comm* c, cudaStream_t stream) {
+  if (!c || !c->connected || c->world <= 1) return GSICP_OK;
+  const unsigned long long seq = ++c->bar_seq;
+  GSICP_LAUNCH(comm_barrier_kernel, 1, 32, 0, stream, c->view(), seq, (int*)nullptr);
+  GSICP_CUDA(cudaGetLastError());
+  return GSICP_OK;
+}
+
+}  // namespace gsicp
+
+using namespace gsicp;
+
+extern "C" int gsicp_comm_alloc(size_t heap_bytes, gsicp_comm** out, void* handle64) {
+  if (!out || !handle64) return GSICP_EINVAL;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+  gsicp_comm* c = new gsicp_comm();
+  GSICP_CUDA(cudaGetDevice(&c->device));
+  c->bytes = kCommHeapOff + ((heap_bytes + 255) & ~size_t(255));
+  if (cudaMalloc((void**)&c->local, c->bytes) != cudaSuccess) {
+    set_error("gsicp_comm_alloc: cudaMalloc(%zu) failed: %s", c->bytes, cudaGetErrorString(cudaGetLastError()));
+    delete c;
+    return GSICP_ENOMEM;
+  }
+  GSICP_CUDA(cudaMemset(c->local, 0, c->bytes));
+  cudaIpcMemHandle_t h;
+  const cudaError_t e = cudaIpcGetMemHandle(&h, c->local);
+  if (e != cudaSuccess) {
+    set_error("gsicp_comm_alloc: cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e));
+    cudaFree(c->local);
+    delete c;
+    return GSICP_ECUDA;
+  }
+  std::memcpy(handle64, &h, 64);
+  *out = c;
+  return GSICP_OK;
+}
+
+extern "C" int gsicp_comm_connect(gsicp_comm* c, int world, int rank, const void* handles) {
+  if (!c || !handles || world < 1 || world > kMaxRanks || rank < 0 || rank >= world) {
+    set_error("gsicp_comm_connect: bad arguments (world %d, rank %d, max %d ranks)", world, rank, kMaxRanks);
+    return GSICP_EINVAL;
+  }
+  c->world = world;
+  c->rank = rank;
+  for (int r = 0; r < world; r++) {
+    if (r == rank) {
+      c->peer[r] = c->local;
+      continue;
+    }
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, (const char*)handles + 64 * (size_t)r, 64);
+    void* p = nullptr;
+    const cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      set_error("gsicp_comm_connect: cudaIpcOpenMemHandle(rank %d) failed: %s", r, cudaGetErrorString(e));
+      return GSICP_ECUDA;
+    }
+    c->peer[r] = (char*)p;
+  }
+  c->connected = true;
+  return GSICP_OK;
+}
+
+extern "C" void gsicp_comm_destroy(gsicp_comm* c) {
+  if (!c) return;
+  for (int r = 0; r < c->world; r++)
+    if (r != c->rank && c->peer[r]) cudaIpcCloseMemHandle(c->peer[r]);
+  if (c->local) cudaFree(c->local);
+  delete c;
+}
+
+extern "C" int gsicp_comm_world(const gsicp_comm* c) { return c ? c->world : 0; }
+extern "C" int gsicp_comm_rank(const gsicp_comm* c) { return c ? c->rank : -1; }
+
+extern "C" int gsicp_comm_barrier(gsicp_comm* c, void* stream) { return comm_stream_barrier(c, (cudaStream_t)stream); }

@@ -28,6 +28,7 @@
 #include <vector>
 
 #include "grid.cuh"
+#include "comm.cuh"
 
 namespace gsicp {
 
@@ -54,15 +55,28 @@ struct CovArgs {
   double* cov;       // [6 * slots]
   float* new_xyz;    // [3 * num_trackable] (only with filter)
   const float* z;    // NULL, or per-point z values: exported scales are divided by max(1, z^1.5 * 2) (fgi:534-538)
+  // multi-GPU (SURVEY §8e "GICP covariance: shard query points"): this rank handles point i iff its covariance slot lies
+  // in [slot_begin, slot_end) — the source range its LM kernel linearises — or, for a point without a slot (untrackable),
+  // iff i lies in [idx_begin, idx_end).  Single GPU: everything.
+  int slot_begin, slot_end, idx_begin, idx_end;
+  __device__ __forceinline__ bool mine(int i) const {
+    if (filter) {
+      const int f = filter[i];
+      if (f > 0) return (f - 1) >= slot_begin && (f - 1) < slot_end;
+      return i >= idx_begin && i < idx_end;
+    }
+    return i >= slot_begin && i < slot_end;
+  }
 };
 
 // k-NN of every point of the cloud in itself, one warp per point: ids and squared distances sorted by (d2, id).
 // The query point itself is its own nearest neighbour (distance 0), as with the reference's kd-tree search.
 template <int K>
 __global__ void __launch_bounds__(128)
-knn_kernel(GridView g, int n, int k, const float* __restrict__ xyz, uint32_t* __restrict__ nn_id, float* __restrict__ nn_d2) {
+knn_kernel(GridView g, int n, int k, const float* __restrict__ xyz, uint32_t* __restrict__ nn_id, float* __restrict__ nn_d2,
+           CovArgs own) {
   const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (i >= n) return;  // warp-uniform
+  if (i >= n || !own.mine(i)) return;  // warp-uniform
   const int lane = threadIdx.x & 31;
   const int kk = min(k, K);
   float d2;
@@ -78,7 +92,7 @@ template <int K>
 __global__ void __launch_bounds__(128, 1)
 covariance_kernel(CovArgs a, const uint32_t* __restrict__ nn_id, const float* __restrict__ nn_d2) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= a.n) return;
+  if (i >= a.n || !a.mine(i)) return;
   const float qx = a.xyz[3 * (size_t)i], qy = a.xyz[3 * (size_t)i + 1], qz = a.xyz[3 * (size_t)i + 2];
   const int kk = min(a.k, K);
   struct { uint32_t id[K]; float d2[K]; } nn;
@@ -163,6 +177,17 @@ covariance_kernel(CovArgs a, const uint32_t* __restrict__ nn_id, const float* __
     a.new_xyz[3 * (size_t)slot + 1] = qy;
     a.new_xyz[3 * (size_t)slot + 2] = qz;
   }
+}
+
+// Sharded runs: every rank keeps the COMPLETE compacted cloud (the k-NN / SVD work is what is sharded, not 12 bytes per point)
+__global__ void compact_xyz_kernel(int n, const int32_t* __restrict__ filter, const float* __restrict__ xyz, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int f = filter[i];
+  if (f <= 0) return;
+  out[3 * (size_t)(f - 1) + 0] = xyz[3 * (size_t)i];
+  out[3 * (size_t)(f - 1) + 1] = xyz[3 * (size_t)i + 1];
+  out[3 * (size_t)(f - 1) + 2] = xyz[3 * (size_t)i + 2];
 }
 
 // covariances from (quaternion, scale) (fgi:828-902)
@@ -512,7 +537,7 @@ struct LmResult {  // lives in mapped pinned host memory; written by block 0
   double lambda;
   int iterations;         // outer iterations run (= value align() returns)
   int converged;
-  int status;             // 0 ok, 1 "lm not converged" (step_lm returned false), 3 grid barrier timed out
+  int status;             // 0 ok, 1 "lm not converged" (step_lm returned false), 3 grid barrier / peer exchange timed out
   int n_lin, n_err;
   int pad;
   unsigned long long seq;
@@ -532,6 +557,8 @@ struct LmArgs {
   double* partL;             // [blocks][28]
   double* partE;             // [2][blocks]
   unsigned int* barrier;     // grid-barrier counter, zero at launch
+  CommView comm;             // multi-GPU: the per-rank sums are exchanged through the peers' segments inside the kernel
+  unsigned long long xseq;   // first exchange sequence number of this launch
   int max_iterations, lm_max_iterations;
   double rot_eps, trans_eps, init_lambda_factor;
   Iso guess;
@@ -651,6 +678,7 @@ align_lm_kernel(LmArgs a) {
   __syncthreads();
 
   unsigned int epoch = 0;  // thread 0's barrier target
+  unsigned long long xseq = a.xseq;
   int iterations = 0, converged = 0, status = 0, n_lin = 0, n_err = 0;
   for (int it = 0; it < a.max_iterations && !converged; it++) {
     iterations = it + 1;
@@ -690,7 +718,21 @@ align_lm_kernel(LmArgs a) {
       status = 3;
       break;
     }
-    reduce_partials<kRed>(a.partL, gridDim.x, s_sum);
+    if (a.comm.active()) {
+      // this rank's sums go to every peer's segment (block 0), then every block of every rank adds the world's slots in
+      // rank order: H, b, y0 are bit-identical on all ranks and the redundant LM decision stays in lock step
+      if (blockIdx.x == 0) {
+        reduce_partials<kRed>(a.partL, gridDim.x, s_sum);
+        comm_lm_publish(a.comm, xseq, s_sum, kRed);
+      }
+      if (!comm_lm_collect(a.comm, xseq, s_sum, kRed)) {
+        status = 3;
+        break;
+      }
+      xseq++;
+    } else {
+      reduce_partials<kRed>(a.partL, gridDim.x, s_sum);
+    }
     n_lin++;
     if (threadIdx.x == 0) {
       int o = 0;
@@ -731,7 +773,19 @@ align_lm_kernel(LmArgs a) {
         break;
       }
       __shared__ double s_yi[1];
-      reduce_partials<1>(a.partE + (size_t)(trial & 1) * gridDim.x, gridDim.x, s_yi);
+      if (a.comm.active()) {
+        if (blockIdx.x == 0) {
+          reduce_partials<1>(a.partE + (size_t)(trial & 1) * gridDim.x, gridDim.x, s_yi);
+          comm_lm_publish(a.comm, xseq, s_yi, 1);
+        }
+        if (!comm_lm_collect(a.comm, xseq, s_yi, 1)) {
+          status = 3;
+          break;
+        }
+        xseq++;
+      } else {
+        reduce_partials<1>(a.partE + (size_t)(trial & 1) * gridDim.x, gridDim.x, s_yi);
+      }
       n_err++;
       if (threadIdx.x == 0) {
         const double yi = s_yi[0];
@@ -853,6 +907,8 @@ struct gsicp_gicp {
   void* h_stage = nullptr;     // pinned staging for H2D conversions
   size_t h_stage_cap = 0;
   int shard_count = 1, shard_index = 0;
+  gsicp_comm* comm = nullptr;    // in-library exchange over peer memory (gsicp_gicp_set_comm); replaces the callback
+  bool src_partial = false;      // sharded covariances: this rank holds only its own source rotations / scales / covariances
   gsicp_allreduce_fn reduce = nullptr;
   void* reduce_user = nullptr;
   bool host_lm = false;          // GSICP_HOST_LM=1: host-driven LM loop (one launch + one spin-wait per phase)
@@ -981,6 +1037,17 @@ struct StageTimer {  // accumulates device time of a stage when timing is enable
   }
 };
 
+void shard_range(const gsicp_gicp* h, int n, int& begin, int& end) {
+  if (h->shard_count <= 1) {
+    begin = 0;
+    end = n;
+    return;
+  }
+  const long long per = ((long long)n + h->shard_count - 1) / h->shard_count;
+  begin = (int)std::min<long long>(n, per * h->shard_index);
+  end = (int)std::min<long long>(n, per * (h->shard_index + 1));
+}
+
 int set_cloud(gsicp_gicp* h, Cloud& c, const void* xyz, int n, int is_f32, bool device_src) {
   if (n < 0 || (n > 0 && !xyz)) {
     set_error("set_input: bad arguments");
@@ -1071,6 +1138,18 @@ int compute_covariances(gsicp_gicp* h, Cloud& c, bool with_filter, bool clamp, b
   a.filter = d_filter; a.xyz = c.xyz.as<float>(); a.rots = c.rots.as<float>(); a.scales = c.scales.as<float>();
   a.cov = c.cov.as<double>(); a.new_xyz = with_filter ? c.xyz_alt.as<float>() : nullptr;
   a.z = withz ? c.zvals.as<float>() : nullptr;
+  // the k-NN + SVD of the SOURCE cloud is sharded over the ranks of the exchange group (each rank needs only the
+  // covariances of the source range it linearises); target covariances are needed everywhere and stay replicated
+  const bool sharded = h->comm && h->shard_count > 1 && (&c == &h->src);
+  a.slot_begin = 0; a.slot_end = slots; a.idx_begin = 0; a.idx_end = n;
+  if (sharded) {
+    shard_range(h, slots, a.slot_begin, a.slot_end);
+    shard_range(h, n, a.idx_begin, a.idx_end);
+    GSICP_CUDA(cudaMemsetAsync(c.rots.ptr, 0, (size_t)n * 4 * sizeof(float), h->stream));  // entries of other ranks: zero (merged on demand)
+    GSICP_CUDA(cudaMemsetAsync(c.scales.ptr, 0, (size_t)n * 3 * sizeof(float), h->stream));
+    GSICP_CUDA(cudaMemsetAsync(c.cov.ptr, 0, (size_t)(slots > 0 ? slots : 1) * 6 * sizeof(double), h->stream));
+  }
+  if (&c == &h->src) h->src_partial = sharded;
   const int grid = (n + 127) / 128;
   if (int e = ensure_grid(h, c)) return e;
   {
@@ -1082,16 +1161,18 @@ int compute_covariances(gsicp_gicp* h, Cloud& c, bool with_filter, bool clamp, b
   float* nd2 = h->nn_d2.as<float>();
   const int kgrid = (int)(((size_t)n * 32 + 127) / 128);
   if (K == 10) {
-    GSICP_LAUNCH(knn_kernel<10>, kgrid, 128, 0, h->stream, c.grid.view(), n, h->k, c.xyz.as<float>(), nid, nd2);
+    GSICP_LAUNCH(knn_kernel<10>, kgrid, 128, 0, h->stream, c.grid.view(), n, h->k, c.xyz.as<float>(), nid, nd2, a);
     GSICP_LAUNCH(covariance_kernel<10>, grid, 128, 0, h->stream, a, nid, nd2);
   } else if (K == 20) {
-    GSICP_LAUNCH(knn_kernel<20>, kgrid, 128, 0, h->stream, c.grid.view(), n, h->k, c.xyz.as<float>(), nid, nd2);
+    GSICP_LAUNCH(knn_kernel<20>, kgrid, 128, 0, h->stream, c.grid.view(), n, h->k, c.xyz.as<float>(), nid, nd2, a);
     GSICP_LAUNCH(covariance_kernel<20>, grid, 128, 0, h->stream, a, nid, nd2);
   } else {
-    GSICP_LAUNCH(knn_kernel<32>, kgrid, 128, 0, h->stream, c.grid.view(), n, h->k, c.xyz.as<float>(), nid, nd2);
+    GSICP_LAUNCH(knn_kernel<32>, kgrid, 128, 0, h->stream, c.grid.view(), n, h->k, c.xyz.as<float>(), nid, nd2, a);
     GSICP_LAUNCH(covariance_kernel<32>, grid, 128, 0, h->stream, a, nid, nd2);
   }
   }
+  if (sharded && with_filter)  // the compacted cloud itself is complete on every rank
+    GSICP_LAUNCH(compact_xyz_kernel, (n + 255) / 256, 256, 0, h->stream, n, d_filter, c.xyz.as<float>(), c.xyz_alt.as<float>());
   GSICP_CUDA(cudaGetLastError());
   c.rots_n = 4 * n;
   c.scales_n = 3 * n;
@@ -1132,17 +1213,6 @@ int covs_from_qs(gsicp_gicp* h, Cloud& c, const float* rots, const float* scales
   c.scales_n = 3 * n;
   c.cov_n = n;
   return GSICP_OK;
-}
-
-void shard_range(const gsicp_gicp* h, int n, int& begin, int& end) {
-  if (h->shard_count <= 1) {
-    begin = 0;
-    end = n;
-    return;
-  }
-  const long long per = ((long long)n + h->shard_count - 1) / h->shard_count;
-  begin = (int)std::min<long long>(n, per * h->shard_index);
-  end = (int)std::min<long long>(n, per * (h->shard_index + 1));
 }
 
 int ensure_lin_buffers(gsicp_gicp* h) {
@@ -1186,6 +1256,65 @@ int wait_published(gsicp_gicp* h, unsigned long long seq) {
       }
     }
   }
+  return GSICP_OK;
+}
+
+// ---- sum-merge of a sharded array over the exchange group (getters of sharded runs; not on the LM path) ----
+// Every rank stages its copy (entries it does not own are zero) in the upper half of its exchange heap; after a barrier
+// each rank adds the world's copies in rank order.  Exact: every entry is non-zero on at most one rank.
+template <typename T>
+__global__ void comm_stage_kernel(size_t count, const T* __restrict__ in, T* __restrict__ stage) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) stage[i] = in[i];
+}
+// correspondences: owned range [begin, end) as index + 1 (so that "unmatched" -1 becomes 0), others 0
+__global__ void comm_stage_corr_kernel(int n, int begin, int end, const int32_t* __restrict__ corr, int32_t* __restrict__ stage) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) stage[i] = (i >= begin && i < end) ? corr[i] + 1 : 0;
+}
+template <typename T>
+__global__ void comm_sum_kernel(CommView c, size_t heap_off, size_t count, T* __restrict__ out, T bias) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  T r = 0;
+  for (int k = 0; k < c.world; k++) {
+    const volatile T* src = reinterpret_cast<const volatile T*>(c.seg[k] + kCommHeapOff + heap_off);
+    r += src[i];
+  }
+  out[i] = r + bias;
+}
+
+template <typename T>
+int comm_sum_merge(gsicp_gicp* h, T* d_buf, size_t count, T bias = 0, const int32_t* corr_src = nullptr, int cb = 0, int ce = 0) {
+  gsicp_comm* c = h->comm;
+  const size_t half = (c->heap_bytes() / 2) & ~size_t(255);
+  if (count * sizeof(T) > half) {
+    set_error("exchange heap too small for a merge of %zu bytes (half heap = %zu)", count * sizeof(T), half);
+    return GSICP_ENOMEM;
+  }
+  T* stage = reinterpret_cast<T*>(c->local + kCommHeapOff + half);
+  const int blocks = (int)((count + 255) / 256);
+  if (corr_src)
+    GSICP_LAUNCH(comm_stage_corr_kernel, blocks, 256, 0, h->stream, (int)count, cb, ce, corr_src, reinterpret_cast<int32_t*>(stage));
+  else
+    GSICP_LAUNCH(comm_stage_kernel<T>, blocks, 256, 0, h->stream, count, d_buf, stage);
+  if (int e = comm_stream_barrier(c, h->stream)) return e;
+  GSICP_LAUNCH(comm_sum_kernel<T>, blocks, 256, 0, h->stream, c->view(), half, count, d_buf, bias);
+  if (int e = comm_stream_barrier(c, h->stream)) return e;  // the staging area may be reused
+  GSICP_CUDA(cudaGetLastError());
+  return GSICP_OK;
+}
+
+// Sharded covariances leave every rank with its own rotations / scales / covariances only: complete them on demand.
+int complete_source_exports(gsicp_gicp* h) {
+  if (!h->src_partial || !h->comm) return GSICP_OK;
+  if (h->src.rots_n > 0)
+    if (int e = comm_sum_merge<float>(h, h->src.rots.as<float>(), (size_t)h->src.rots_n)) return e;
+  if (h->src.scales_n > 0)
+    if (int e = comm_sum_merge<float>(h, h->src.scales.as<float>(), (size_t)h->src.scales_n)) return e;
+  if (h->src.cov_n > 0)
+    if (int e = comm_sum_merge<double>(h, h->src.cov.as<double>(), (size_t)h->src.cov_n * 6)) return e;
+  h->src_partial = false;
   return GSICP_OK;
 }
 
@@ -1366,6 +1495,16 @@ int run_align_device(gsicp_gicp* h, Iso& x0) {
   a.corr = h->corr.as<int32_t>(); a.sqd = h->sqd.as<float>(); a.mahal = h->mahal.as<double>();
   a.partL = h->lm_partL.as<double>(); a.partE = h->lm_partE.as<double>();
   a.barrier = h->lm_barrier.as<unsigned int>();
+  a.comm = CommView();
+  a.xseq = 0;
+  if (h->comm && h->shard_count > 1) {
+    a.comm = h->comm->view();
+    // an align runs at most max_iterations * (1 + lm_max_iterations) exchanges; the base advances by a bound that every
+    // rank computes identically, so sequence numbers stay monotone across launches
+    const unsigned long long bound = (unsigned long long)std::max(1, h->max_iterations) * (unsigned long long)(1 + std::max(1, h->lm_max_iterations));
+    a.xseq = h->comm->lm_seq + 2;
+    h->comm->lm_seq += (bound + 3) & ~1ull;
+  }
   a.max_iterations = h->max_iterations; a.lm_max_iterations = h->lm_max_iterations;
   a.rot_eps = h->rot_eps; a.trans_eps = h->trans_eps; a.init_lambda_factor = h->lm_init_lambda_factor;
   a.guess = x0;
@@ -1576,7 +1715,7 @@ int gsicp_gicp_align(gsicp_gicp* h, const float guess[16], float out[16]) {
   }
   h->lm_lambda = -1.0;
   int iters = 0;
-  if (!h->host_lm && !h->timing && h->shard_count <= 1) {
+  if (!h->host_lm && !h->timing && (h->shard_count <= 1 || h->comm)) {
     // device-resident LM loop: one persistent kernel, zero host round trips inside the loop
     if (h->d_lm) std::memset(h->h_lm->H, 0, sizeof(h->h_lm->H));
     iters = run_align_device(h, x0);
@@ -1614,11 +1753,11 @@ int gsicp_gicp_source_rotationsq_size(gsicp_gicp* h) { H_CHECK(h); return h->src
 int gsicp_gicp_target_rotationsq_size(gsicp_gicp* h) { H_CHECK(h); return h->tgt.rots_n; }
 int gsicp_gicp_source_scales_size(gsicp_gicp* h) { H_CHECK(h); return h->src.scales_n; }
 int gsicp_gicp_target_scales_size(gsicp_gicp* h) { H_CHECK(h); return h->tgt.scales_n; }
-int gsicp_gicp_get_source_rotationsq(gsicp_gicp* h, float* o) { H_CHECK(h); return copy_out(h, h->src.rots, (size_t)h->src.rots_n * 4, o); }
+int gsicp_gicp_get_source_rotationsq(gsicp_gicp* h, float* o) { H_CHECK(h); if (int e = complete_source_exports(h)) return e; return copy_out(h, h->src.rots, (size_t)h->src.rots_n * 4, o); }
 int gsicp_gicp_get_target_rotationsq(gsicp_gicp* h, float* o) { H_CHECK(h); return copy_out(h, h->tgt.rots, (size_t)h->tgt.rots_n * 4, o); }
-int gsicp_gicp_get_source_scales(gsicp_gicp* h, float* o) { H_CHECK(h); return copy_out(h, h->src.scales, (size_t)h->src.scales_n * 4, o); }
+int gsicp_gicp_get_source_scales(gsicp_gicp* h, float* o) { H_CHECK(h); if (int e = complete_source_exports(h)) return e; return copy_out(h, h->src.scales, (size_t)h->src.scales_n * 4, o); }
 int gsicp_gicp_get_target_scales(gsicp_gicp* h, float* o) { H_CHECK(h); return copy_out(h, h->tgt.scales, (size_t)h->tgt.scales_n * 4, o); }
-int gsicp_gicp_get_source_covariances(gsicp_gicp* h, double* o) { H_CHECK(h); return copy_cov_out(h, h->src, o); }
+int gsicp_gicp_get_source_covariances(gsicp_gicp* h, double* o) { H_CHECK(h); if (int e = complete_source_exports(h)) return e; return copy_cov_out(h, h->src, o); }
 int gsicp_gicp_get_target_covariances(gsicp_gicp* h, double* o) { H_CHECK(h); return copy_cov_out(h, h->tgt, o); }
 
 int gsicp_gicp_get_source_correspondence(gsicp_gicp* h, int32_t* corr, float* sq_dist) {
@@ -1631,7 +1770,15 @@ int gsicp_gicp_get_source_correspondence(gsicp_gicp* h, int32_t* corr, float* sq
   }
   if (h->src.n == 0) return GSICP_OK;
   if (!corr || !sq_dist) return GSICP_EINVAL;
-  if (h->shard_count > 1 && h->reduce) {  // merge the ranks' ranges (gathered only when asked for)
+  if (h->shard_count > 1 && h->comm) {  // merge the ranks' ranges through the exchange heap (only when asked for)
+    int begin, end;
+    shard_range(h, h->src.n, begin, end);
+    if (int e = comm_sum_merge<int32_t>(h, h->corr.as<int32_t>(), (size_t)h->src.n, -1, h->corr.as<int32_t>(), begin, end)) return e;
+    // squared distances: zero outside the own range, then summed
+    GSICP_CUDA(cudaMemsetAsync(h->sqd.as<float>(), 0, (size_t)begin * 4, h->stream));
+    if (end < h->src.n) GSICP_CUDA(cudaMemsetAsync(h->sqd.as<float>() + end, 0, (size_t)(h->src.n - end) * 4, h->stream));
+    if (int e = comm_sum_merge<float>(h, h->sqd.as<float>(), (size_t)h->src.n)) return e;
+  } else if (h->shard_count > 1 && h->reduce) {  // merge the ranks' ranges (gathered only when asked for)
     const int n = h->src.n;
     int begin, end;
     shard_range(h, n, begin, end);
@@ -1725,6 +1872,22 @@ int gsicp_gicp_set_shard(gsicp_gicp* h, int count, int index, gsicp_allreduce_fn
   if (count < 1 || index < 0 || index >= count) return GSICP_EINVAL;
   h->shard_count = count; h->shard_index = index; h->reduce = reduce; h->reduce_user = user;
   h->corr_n = -1;
+  return GSICP_OK;
+}
+
+int gsicp_gicp_set_comm(gsicp_gicp* h, gsicp_comm* comm) {
+  H_CHECK(h);
+  if (comm && !comm->connected) {
+    set_error("gsicp_gicp_set_comm: the exchange group is not connected");
+    return GSICP_ESTATE;
+  }
+  h->comm = comm;
+  h->shard_count = comm ? comm->world : 1;
+  h->shard_index = comm ? comm->rank : 0;
+  h->reduce = nullptr;
+  h->reduce_user = nullptr;
+  h->corr_n = -1;
+  h->src.clear_cov();
   return GSICP_OK;
 }
 

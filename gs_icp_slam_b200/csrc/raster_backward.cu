@@ -57,12 +57,11 @@ __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__flo
 //   [6..8]  sum v {1, dx, dy}                         v = w dL/dpix_depth, w = alpha T   ([6] = dL/ddepth)
 //   [9..11] sum w dL/dpix_{r,g,b}                                                         (= dL/dcolour)
 // gaussian_backward_kernel forms the reference's gradients from them with per-Gaussian coefficients.
-// kPipe: software-pipelined survivor loop — the alpha evaluation of candidate k+1 (shared-memory reads, expf: independent
-// of the blend state) and the transmittance / accumulator chain of candidate k are issued from ONE branch-free basic
-// block, so the instruction scheduler interleaves the two dependent chains (the kernel is bound by dependent-issue
-// latency at 5 warps per scheduler, profiles/r2a_ncu_top_kernels.txt).  kMinBlocks: CTAs per SM the register budget targets.
-template <bool kCull, bool kPipe, int kMinBlocks>
-__global__ void __launch_bounds__(kTilePixels, kMinBlocks)
+// Measured and dropped (profiles/r2b_notes.md): a software-pipelined survivor loop (alpha evaluation of candidate k+1
+// interleaved with the blend chain of candidate k in one predicated basic block: 240 us vs 226 us) and a 128-register /
+// 2-CTA-per-SM build (262-276 us): the kernel wants resident warps, not more ILP per warp.
+template <bool kCull>
+__global__ void __launch_bounds__(kTilePixels, 3)
 render_backward_kernel(const uint32_t* __restrict__ tile_order, const uint2* __restrict__ ranges,
                        const uint32_t* __restrict__ point_list, int W, int H,
                        int tiles_x, const float* __restrict__ bg, const Splat* __restrict__ splats,
@@ -238,57 +237,6 @@ render_backward_kernel(const uint32_t* __restrict__ tile_order, const uint2* __r
         if (kCull) hit = hit && subtile_hit(sA[j < n ? j : 0], sB[j < n ? j : 0], wx0f, wy0f, 7.f, 3.f);
         mask = __ballot_sync(0xffffffffu, hit);
       }
-      if constexpr (kPipe) {
-        // pending candidate (warp-uniform validity): everything the blend chain needs from the evaluation stage
-        bool pending = false, p_active = false;
-        float p_G = 0.f, p_alpha = 0.f, p_depth = 0.f, p_r = 0.f, p_g = 0.f, p_b = 0.f;
-        int p_j = 0;
-        while (mask || pending) {
-          // ---- stage E: evaluate the next candidate (slot 0 is read harmlessly when the list is exhausted) ----
-          const bool has = mask != 0;
-          const int bit = has ? (__ffs(mask) - 1) : 0;
-          mask &= mask - 1;
-          const int j = has ? (c0 + bit) : 0;
-          const int contributor = first_pos - j;
-          const float4 a = sA[j], b = sB[j], c = sC[j];
-          const float dx = a.x - pxf, dy = a.y - pyf;
-          const float power = -0.5f * (a.z * dx * dx + b.x * dy * dy) - a.w * dx * dy;
-          const float G = expf(power);
-          const float alpha = fminf(0.99f, b.y * G);
-          const float depth = c.w - (b.z * a.z + b.w * a.w) * dx - (b.z * a.w + b.w * b.x) * dy;
-          const bool e_active = has && inside && (contributor <= last_contributor) && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
-          // ---- stage C: blend chain of the pending candidate, predicated (same expressions as the branchy loop) ----
-          const bool act = pending && p_active;
-          const float inv = __frcp_rn(1.f - p_alpha);
-          const float Tn = T * inv;
-          const float n_r = last_alpha * last_r + (1.f - last_alpha) * acc_r;
-          const float n_g = last_alpha * last_g + (1.f - last_alpha) * acc_g;
-          const float n_b = last_alpha * last_b + (1.f - last_alpha) * acc_b;
-          const float n_d = last_alpha * last_depth + (1.f - last_alpha) * acc_d;
-          const float dsum = ((p_r - n_r) * dpr + (p_g - n_g) * dpg + (p_b - n_b) * dpb + (p_depth - n_d) * dpd) * Tn - bg_term * inv;
-          const float tq = act ? p_G * dsum : 0.f;
-          const float wq = act ? p_alpha * Tn : 0.f;
-          T = act ? Tn : T;
-          acc_r = act ? n_r : acc_r; acc_g = act ? n_g : acc_g; acc_b = act ? n_b : acc_b; acc_d = act ? n_d : acc_d;
-          last_r = act ? p_r : last_r; last_g = act ? p_g : last_g; last_b = act ? p_b : last_b;
-          last_depth = act ? p_depth : last_depth;
-          last_alpha = act ? p_alpha : last_alpha;
-          if (pending) {
-            myT[cnt * kRow + wpos] = tq;
-            myW[cnt * kRow + wpos] = wq;
-            if (lane == cnt) {
-              const float4 pa = sA[p_j];
-              m_cx = pa.x - wx0f;
-              m_cy = pa.y - wy0f;
-              m_id = point_list[range.y - 1 - base - p_j];
-            }
-            if (++cnt == kGrp) flush();
-          }
-          // ---- rotate: the evaluated candidate becomes pending when any pixel of the sub-tile blends it ----
-          pending = __any_sync(0xffffffffu, e_active);
-          p_active = e_active; p_G = G; p_alpha = alpha; p_depth = depth; p_r = c.x; p_g = c.y; p_b = c.z; p_j = j;
-        }
-      } else
       while (mask) {
         const int bit = __ffs(mask) - 1;
         mask &= mask - 1;
@@ -631,9 +579,6 @@ gaussian_backward_kernel(BwdArgs a, const int32_t* __restrict__ radii, const uin
 }
 
 extern int g_render_cull;
-// render_backward variant (GSICP_BWD_VARIANT / gsicp_test_set_bwd_variant): 0 = branchy loop, 3 CTAs/SM; 1 = pipelined loop,
-// 3 CTAs/SM; 2 = pipelined, 2 CTAs/SM (128 registers); 3 = branchy, 2 CTAs/SM.  All variants compute the same sums.
-int g_bwd_variant = [] { const char* e = getenv("GSICP_BWD_VARIANT"); return e ? atoi(e) : 0; }();
 
 // ---- multi-GPU: all-reduce of the render moments of the VISIBLE Gaussians ----
 // Every rank preprocesses all Gaussians, so the set {radii > 0} and its index order are identical on all ranks: the
@@ -739,12 +684,8 @@ static int ensure_bwd_smem_attr() {
   GSICP_CUDA(cudaGetDevice(&dev));
   std::lock_guard<std::mutex> lock(mu);
   if (dev < 0 || dev >= 64 || done[dev]) return GSICP_OK;
-  const int bytes = (int)sizeof(BwdSmem);
-  GSICP_CUDA(cudaFuncSetAttribute(render_backward_kernel<false, false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-  GSICP_CUDA(cudaFuncSetAttribute(render_backward_kernel<true, false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-  GSICP_CUDA(cudaFuncSetAttribute(render_backward_kernel<true, true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-  GSICP_CUDA(cudaFuncSetAttribute(render_backward_kernel<true, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-  GSICP_CUDA(cudaFuncSetAttribute(render_backward_kernel<true, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  GSICP_CUDA(cudaFuncSetAttribute(render_backward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BwdSmem)));
+  GSICP_CUDA(cudaFuncSetAttribute(render_backward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BwdSmem)));
   done[dev] = true;
   return GSICP_OK;
 }
@@ -791,19 +732,15 @@ extern "C" int gsicp_raster_backward(const gsicp_raster_args* args, int num_rend
   if (num_rendered > 0) {
     if (int e = ensure_bwd_smem_attr()) return e;
     ProfScope ps(kProfRenderBwd, stream);
-#define GSICP_BWD_LAUNCH(CULL, PIPE, MINB)                                                                                 \
-  GSICP_LAUNCH((render_backward_kernel<CULL, PIPE, MINB>), tiles, kTilePixels, sizeof(BwdSmem), stream, img.tile_order,   \
-               img.ranges, bin.point_list, W, H, tiles_x, args->d_background, geom.splats, img.final_T, img.n_contrib,    \
-               d_dL_dout_color, d_dL_dout_depth, work, shard_count, shard_index)
-    const int variant = g_render_cull ? g_bwd_variant : -1;
-    switch (variant) {
-      case -1: GSICP_BWD_LAUNCH(false, false, 3); break;  // test hook: no sub-tile culling
-      case 1: GSICP_BWD_LAUNCH(true, true, 3); break;
-      case 2: GSICP_BWD_LAUNCH(true, true, 2); break;
-      case 3: GSICP_BWD_LAUNCH(true, false, 2); break;
-      default: GSICP_BWD_LAUNCH(true, false, 3); break;
+    if (g_render_cull) {
+      GSICP_LAUNCH(render_backward_kernel<true>, tiles, kTilePixels, sizeof(BwdSmem), stream, img.tile_order, img.ranges, bin.point_list,
+                   W, H, tiles_x, args->d_background, geom.splats, img.final_T, img.n_contrib, d_dL_dout_color, d_dL_dout_depth,
+                   work, shard_count, shard_index);
+    } else {  // test hook: no sub-tile culling
+      GSICP_LAUNCH(render_backward_kernel<false>, tiles, kTilePixels, sizeof(BwdSmem), stream, img.tile_order, img.ranges, bin.point_list,
+                   W, H, tiles_x, args->d_background, geom.splats, img.final_T, img.n_contrib, d_dL_dout_color, d_dL_dout_depth,
+                   work, shard_count, shard_index);
     }
-#undef GSICP_BWD_LAUNCH
     if (args->debug) GSICP_CUDA(cudaStreamSynchronize(stream));
   }
 
@@ -827,5 +764,3 @@ extern "C" int gsicp_raster_backward(const gsicp_raster_args* args, int num_rend
   GSICP_CUDA(cudaGetLastError());
   return GSICP_OK;
 }
-
-extern "C" void gsicp_test_set_bwd_variant(int v) { gsicp::g_bwd_variant = v; }

@@ -224,6 +224,26 @@ typedef int (*gsicp_allreduce_fn)(void* user, double* d_buf, int count, void* st
 int gsicp_gicp_set_shard(gsicp_gicp*, int shard_count, int shard_index,
                          gsicp_allreduce_fn reduce, void* user);
 
+/* ---- Multi-GPU exchange group (one process per GPU; replaces the survey sketch's gsicp_gicp_comm_init(ncclComm_t)) ----
+ * Each rank allocates a symmetric device segment and exports it as a 64-byte CUDA IPC handle; after the application
+ * has exchanged the handles (any channel: torch.distributed.all_gather_object in the Python host code), every rank
+ * maps its peers' segments (NVLink peer access).  The kernels then exchange their partial sums by writing straight into
+ * the peers' segments and polling sequence flags: no host hop and no second kernel per exchange.
+ *   GICP:        source points (LM linearisation AND k-NN covariances) are sharded over the ranks; the 28-double normal
+ *                equations / the 1-double error are exchanged inside the persistent LM kernel (fgi:296-378).
+ *   rasterizer:  screen tiles are sharded; the per-Gaussian render moments accumulate in the segment and every rank adds
+ *                the world's rows of the visible Gaussians in rank order inside gsicp_raster_backward.
+ * heap_bytes: per-rank exchange heap (>= 96 bytes per Gaussian for the rasterizer; merges of sharded getters use its upper half). */
+typedef struct gsicp_comm gsicp_comm;
+int gsicp_comm_alloc(size_t heap_bytes, gsicp_comm** out, void* handle64);
+int gsicp_comm_connect(gsicp_comm*, int world, int rank, const void* handles /* world x 64 bytes, rank order */);
+void gsicp_comm_destroy(gsicp_comm*);
+int gsicp_comm_world(const gsicp_comm*);
+int gsicp_comm_rank(const gsicp_comm*);
+int gsicp_comm_barrier(gsicp_comm*, void* stream);   /* stream-ordered barrier over the group */
+int gsicp_gicp_set_comm(gsicp_gicp*, gsicp_comm*);    /* NULL: back to single-GPU */
+int gsicp_raster_set_comm(gsicp_comm*);               /* NULL: back to single-GPU; also sets the tile shard (count, index) */
+
 /* Stream on which the handle's kernels run (default: legacy default stream 0). */
 int gsicp_gicp_set_stream(gsicp_gicp*, void* stream);
 /* Test / A-B hook: 1 = drive the LM loop from the host (one launch + one wait per linearize / compute_error), 0 (default) =
