@@ -250,10 +250,10 @@ class Ours:
             from gs_icp_slam_b200 import sharding
 
             self.sharding = sharding
-            rasterizer.set_tile_shard(world, rank)
-            rasterizer.set_allreduce(sharding.make_raster_allreduce(dev))  # moments of the visible Gaussians, inside backward
+            self.group = sharding.ShardGroup(dev, world, rank)  # in-kernel exchange over peer memory (NCCL callbacks as fallback)
+            self.group.attach_rasterizer()
+            self.group.attach_gicp(self.reg)
             self.pix_mask = sharding.tile_owner_mask(H, W, world, rank, dev)
-            self.reg.set_shard(world, rank, sharding.make_gicp_allreduce(dev))
         self.pose = frames[0]["c2w"].astype(np.float32)
         self.pool = None
         self.gicp_stream = None
@@ -382,6 +382,9 @@ class Ours:
         """Orderly teardown (worker thread, library handle) before the interpreter exits normally."""
         self.enable_concurrent(False)
         self.torch.cuda.synchronize()
+        if getattr(self, "group", None) is not None:
+            self.group.close()
+            self.group = None
         self.reg = None
 
     def run(self, steps, warmup, resident, profile=False):
@@ -786,7 +789,7 @@ def main():
                                               ((kernels["render_forward"]["ms_per_launch"] + kernels["render_backward"]["ms_per_launch"]) * 1e-3))
 
     parallelism = ("single GPU" if world == 1 else
-                   f"{world} GPUs, one sequence, raster tiles + GICP source points sharded" if shard else
+                   f"{world} GPUs, one sequence, raster tiles + GICP source points sharded, in-library exchange over peer memory" if shard else
                    f"{world} independent SLAM sequences (replicas), one per GPU, no collective")
     out = {"metric": METRIC, "value": fps(t_res), "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm,
            "ms_per_step": t_res / K, "higher_is_better": True, "scaling": "strong" if shard else "weak", "vs_baseline": None,

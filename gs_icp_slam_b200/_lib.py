@@ -120,6 +120,14 @@ _sig("gsicp_gicp_compute_error", i32, [vp, vp, vp])
 _sig("gsicp_gicp_set_shard", i32, [vp, i32, i32, ALLREDUCE_FN, vp])
 _sig("gsicp_gicp_set_stream", i32, [vp, vp])
 _sig("gsicp_gicp_set_host_lm", i32, [vp, i32])
+_sig("gsicp_comm_alloc", i32, [C.c_size_t, C.POINTER(vp), vp])
+_sig("gsicp_comm_connect", i32, [vp, i32, i32, vp])
+_sig("gsicp_comm_destroy", None, [vp])
+_sig("gsicp_comm_world", i32, [vp])
+_sig("gsicp_comm_rank", i32, [vp])
+_sig("gsicp_comm_barrier", i32, [vp, vp])
+_sig("gsicp_gicp_set_comm", i32, [vp, vp])
+_sig("gsicp_raster_set_comm", i32, [vp])
 _sig("gsicp_mapping_loss_work_bytes", C.c_size_t, [i32, i32])
 _sig("gsicp_mapping_loss_forward", i32, [i32, i32, vp, vp, vp, vp, C.c_float, C.c_float, C.c_float, i32, vp, vp, vp, vp, vp])
 _sig("gsicp_mapping_loss_backward", i32, [i32, i32, vp, vp, vp, vp, C.c_float, C.c_float, C.c_float, i32, vp, vp, vp, vp, vp])

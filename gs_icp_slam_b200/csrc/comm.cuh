@@ -110,7 +110,8 @@ struct gsicp_comm {
   char* peer[gsicp::kMaxRanks] = {};
   bool connected = false;
   unsigned long long bar_seq = 0;  // stream-barrier sequence (host-side counter; identical call order on every rank)
-  unsigned long long lm_seq = 0;   // LM exchange sequence base (advanced by the upper bound of exchanges per align)
+  unsigned long long lm_seq = 0;   // last LM exchange sequence number handed out (host-side, identical on every rank)
+  bool lm_resync = false;          // the last launch consumed a data-dependent number of exchanges: re-align with a barrier
   gsicp::CommView view() const {
     gsicp::CommView v;
     v.world = world;

@@ -239,8 +239,10 @@ template <int NV>
 __device__ __forceinline__ void block_reduce_finalize(double* v, double* __restrict__ partial, double* __restrict__ out,
                                                       unsigned int* __restrict__ counter, double* host_out = nullptr,
                                                       volatile unsigned long long* host_seq = nullptr,
-                                                      unsigned long long seq = 0) {
+                                                      unsigned long long seq = 0, CommView comm = CommView(),
+                                                      unsigned long long xseq = 0) {
   __shared__ double s_red[kLinBlock / 32][NV];
+  __shared__ double s_tot[NV];
   __shared__ bool s_last;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -267,8 +269,18 @@ __device__ __forceinline__ void block_reduce_finalize(double* v, double* __restr
     if (threadIdx.x < NV) {
       double r = 0.0;
       for (unsigned int b = 0; b < gridDim.x; b++) r += partial[(size_t)b * NV + threadIdx.x];
-      out[threadIdx.x] = r;
-      if (host_out) host_out[threadIdx.x] = r;
+      s_tot[threadIdx.x] = r;
+    }
+    __syncthreads();
+    if (comm.active()) {
+      // multi-GPU: the last block exchanges this rank's sums with the peers through their segments (comm.cuh) and adds
+      // the world's slots in rank order — the result the host reads is already the global one, bit-identical on all ranks
+      comm_lm_publish(comm, xseq, s_tot, NV);
+      comm_lm_collect(comm, xseq, s_tot, NV);  // a lost peer leaves the local sums in place after the poll budget
+    }
+    if (threadIdx.x < NV) {
+      out[threadIdx.x] = s_tot[threadIdx.x];
+      if (host_out) host_out[threadIdx.x] = s_tot[threadIdx.x];
     }
     if (host_out) {
       __threadfence_system();
@@ -300,6 +312,8 @@ struct LinArgs {
   double* host_out;        // mapped pinned [28] or null
   volatile unsigned long long* host_seq;
   unsigned long long seq;
+  CommView comm;             // multi-GPU: exchange inside the last block
+  unsigned long long xseq;
 };
 
 // Correspondence search (fgi:242-272): one WARP per source point.  fp32 transform of the query, exact 1-NN in the
@@ -478,7 +492,7 @@ linearize_kernel(PoseD T, LinArgs a) {
     const int32_t j = a.corr[i];
     if (j >= 0) linearize_point(T, i, j, a.src_xyz, a.src_cov, a.tgt_xyz, a.tgt_cov, a.mahal, v);
   }
-  block_reduce_finalize<kRed>(v, a.partial, a.out, a.counter, a.host_out, a.host_seq, a.seq);
+  block_reduce_finalize<kRed>(v, a.partial, a.out, a.counter, a.host_out, a.host_seq, a.seq, a.comm, a.xseq);
 }
 
 struct ErrArgs {
@@ -493,6 +507,8 @@ struct ErrArgs {
   double* host_out;
   volatile unsigned long long* host_seq;
   unsigned long long seq;
+  CommView comm;
+  unsigned long long xseq;
 };
 
 __global__ void __launch_bounds__(kLinBlock)
@@ -503,7 +519,7 @@ error_kernel(PoseD T, ErrArgs a) {
     const int32_t j = a.corr[i];
     if (j >= 0) v[0] = error_point(T, i, j, a.src_xyz, a.tgt_xyz, a.mahal);
   }
-  block_reduce_finalize<1>(v, a.partial, a.out, a.counter, a.host_out, a.host_seq, a.seq);
+  block_reduce_finalize<1>(v, a.partial, a.out, a.counter, a.host_out, a.host_seq, a.seq, a.comm, a.xseq);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -529,7 +545,8 @@ error_kernel(PoseD T, ErrArgs a) {
 constexpr int kLmBlock = 256;     // threads per block of align_lm_kernel
 constexpr int kLmChunk = 4;       // source points per warp visit
 constexpr int kLmSeg = 8;         // partial-sum segments per value in the cross-block reduction
-constexpr long long kLmPollBudget = 1ll << 27;  // barrier polls before giving up (seconds of wall time)
+constexpr long long kLmPollBudget = 1ll << 27;
+constexpr int kLmPersistentMax = 65536;  // source points per rank up to which the persistent LM kernel is used  // barrier polls before giving up (seconds of wall time)
 
 struct LmResult {  // lives in mapped pinned host memory; written by block 0
   double R[9], t[3];      // final pose x0
@@ -1318,6 +1335,22 @@ int complete_source_exports(gsicp_gicp* h) {
   return GSICP_OK;
 }
 
+// Exchange sequence numbers (comm.cuh): consecutive exchanges must alternate the parity slot.  A host-driven kernel
+// consumes exactly one number; the persistent LM kernel consumes a data-dependent count from a reserved range, so a
+// stream barrier re-aligns the ranks before and after it (every rank has finished reading the slots of the previous
+// launch before any rank writes them again).
+int comm_take_seq(gsicp_gicp* h, unsigned long long reserve, unsigned long long* first) {
+  gsicp_comm* c = h->comm;
+  if (c->lm_resync || reserve > 1) {
+    if (int e = comm_stream_barrier(c, h->stream)) return e;
+    c->lm_resync = false;
+  }
+  *first = c->lm_seq + 1;
+  c->lm_seq += reserve;
+  if (reserve > 1) c->lm_resync = true;
+  return GSICP_OK;
+}
+
 // fgi:296-352.  H may be null (error only).
 int run_linearize(gsicp_gicp* h, const Iso& x, double H[6][6], double b[6], double* err) {
   if (int e = ensure_lin_buffers(h)) return e;
@@ -1337,10 +1370,17 @@ int run_linearize(gsicp_gicp* h, const Iso& x, double H[6][6], double b[6], doub
   a.tgt_xyz = h->tgt.xyz.as<float>(); a.tgt_cov = h->tgt.cov.as<double>();
   a.corr = h->corr.as<int32_t>(); a.sqd = h->sqd.as<float>(); a.mahal = h->mahal.as<double>();
   a.partial = h->partial.as<double>(); a.out = h->red_out.as<double>(); a.counter = h->counter.as<unsigned int>();
-  const bool direct = (h->shard_count <= 1) && !h->timing;  // publish straight into mapped host memory
+  const bool xchg = h->shard_count > 1 && h->comm;  // in-kernel exchange: the published sums are already global
+  const bool direct = (h->shard_count <= 1 || xchg) && !h->timing;  // publish straight into mapped host memory
   a.host_out = direct ? (double*)h->d_map : nullptr;
   a.host_seq = direct ? (volatile unsigned long long*)(h->d_map + 28) : nullptr;
   a.seq = ++h->seq;
+  a.comm = CommView();
+  a.xseq = 0;
+  if (xchg) {
+    a.comm = h->comm->view();
+    if (int e = comm_take_seq(h, 1, &a.xseq)) return e;
+  }
   int blocks = (end - begin + kLinBlock - 1) / kLinBlock;
   if (blocks < 1) blocks = 1;
   if (end > begin)
@@ -1393,10 +1433,17 @@ int run_error(gsicp_gicp* h, const Iso& x, double* err) {  // fgi:355-378
   a.src_xyz = h->src.xyz.as<float>(); a.tgt_xyz = h->tgt.xyz.as<float>();
   a.corr = h->corr.as<int32_t>(); a.mahal = h->mahal.as<double>();
   a.partial = h->partial.as<double>(); a.out = h->red_out.as<double>(); a.counter = h->counter.as<unsigned int>();
-  const bool direct = (h->shard_count <= 1) && !h->timing;
+  const bool xchg = h->shard_count > 1 && h->comm;
+  const bool direct = (h->shard_count <= 1 || xchg) && !h->timing;
   a.host_out = direct ? (double*)h->d_map : nullptr;
   a.host_seq = direct ? (volatile unsigned long long*)(h->d_map + 28) : nullptr;
   a.seq = ++h->seq;
+  a.comm = CommView();
+  a.xseq = 0;
+  if (xchg) {
+    a.comm = h->comm->view();
+    if (int e = comm_take_seq(h, 1, &a.xseq)) return e;
+  }
   int blocks = (end - begin + kLinBlock - 1) / kLinBlock;
   if (blocks < 1) blocks = 1;
   { ProfScope ps(kProfError, h->stream);
@@ -1499,17 +1546,10 @@ int run_align_device(gsicp_gicp* h, Iso& x0) {
   a.xseq = 0;
   if (h->comm && h->shard_count > 1) {
     a.comm = h->comm->view();
-    // an align runs at most max_iterations * (1 + lm_max_iterations) exchanges; the base advances by a bound that every
-    // rank computes identically, so sequence numbers stay monotone across launches
+    // an align runs at most max_iterations * (1 + lm_max_iterations) exchanges: reserve that many sequence numbers
     const unsigned long long bound = (unsigned long long)std::max(1, h->max_iterations) * (unsigned long long)(1 + std::max(1, h->lm_max_iterations));
-    a.xseq = h->comm->lm_seq + 2;
-    h->comm->lm_seq += (bound + 3) & ~1ull;
+    if (int e = comm_take_seq(h, bound + 1, &a.xseq)) return e;
   }
-  a.max_iterations = h->max_iterations; a.lm_max_iterations = h->lm_max_iterations;
-  a.rot_eps = h->rot_eps; a.trans_eps = h->trans_eps; a.init_lambda_factor = h->lm_init_lambda_factor;
-  a.guess = x0;
-  a.result = h->d_lm;
-  a.seq = ++h->seq;
   {
     ProfScope ps(kProfLinearize, h->stream);  // slot "gicp_linearize": the whole device-resident LM loop
     GSICP_LAUNCH(align_lm_kernel, blocks, kLmBlock, 0, h->stream, a);
@@ -1715,7 +1755,12 @@ int gsicp_gicp_align(gsicp_gicp* h, const float guess[16], float out[16]) {
   }
   h->lm_lambda = -1.0;
   int iters = 0;
-  if (!h->host_lm && !h->timing && (h->shard_count <= 1 || h->comm)) {
+  int lb, le;
+  shard_range(h, h->src.n, lb, le);
+  // The persistent kernel (one block per SM) wins where launch / wait latency dominates; above kLmPersistentMax points per
+  // rank the phases are throughput-bound and the full-occupancy kernels of the host-driven loop are faster
+  // (in a sharded run their last block exchanges through the peers' segments as well: no host-side collective either way).
+  if (!h->host_lm && !h->timing && (h->shard_count <= 1 || h->comm) && (le - lb) <= kLmPersistentMax) {
     // device-resident LM loop: one persistent kernel, zero host round trips inside the loop
     if (h->d_lm) std::memset(h->h_lm->H, 0, sizeof(h->h_lm->H));
     iters = run_align_device(h, x0);

@@ -23,6 +23,7 @@
 #include <mutex>
 #include "host_common.h"
 #include "raster_common.cuh"
+#include "comm.cuh"
 
 namespace gsicp {
 
@@ -371,7 +372,7 @@ gaussian_backward_kernel(BwdArgs a, const int32_t* __restrict__ radii, const uin
                          float* __restrict__ dL_dmean2D, float* __restrict__ dL_dcolors,
                          float* __restrict__ dL_dopacity, float* __restrict__ dL_dmeans3D,
                          float* __restrict__ dL_dcov3D, float* __restrict__ dL_dsh, float* __restrict__ dL_dscales,
-                         float* __restrict__ dL_drots) {
+                         float* __restrict__ dL_drots, float* __restrict__ xmom) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= a.P) return;
   // dL_dmean2D is [P][3]; the third component is never written by the reference either (stays zero)
@@ -413,6 +414,10 @@ gaussian_backward_kernel(BwdArgs a, const int32_t* __restrict__ radii, const uin
   float4* mrow = reinterpret_cast<float4*>(moments) + 3 * (size_t)idx;
   const float4 m0 = mrow[0], m1 = mrow[1], m2 = mrow[2];
   mrow[0] = mrow[1] = mrow[2] = make_float4(0.f, 0.f, 0.f, 0.f);  // consumed: a second backward on the same state starts from zero
+  if (xmom) {  // sharded run: this rank's accumulator row in the exchange segment (every peer has read it by now)
+    float4* xr = reinterpret_cast<float4*>(xmom) + 3 * (size_t)idx;
+    xr[0] = xr[1] = xr[2] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   const Splat sp = splats[idx];
   const float cA = sp.a.z, cB = sp.a.w, cC = sp.b.x, opac = sp.b.y, czx = sp.b.z, cyz = sp.b.w;
   // u = opacity * t (backward.cu:606-612 multiply by con_o.w per pair; here once per Gaussian)
@@ -612,6 +617,35 @@ __global__ void moments_compact_kernel(int P, const int32_t* __restrict__ radii,
   }
 }
 
+// Sharded run through the exchange layer (comm.cuh): every rank's render_backward accumulated the moments of ITS tiles in
+// its own segment; after a barrier each rank adds the world's rows of the visible Gaussians in rank order (P2P loads over
+// NVLink, 48 B per visible Gaussian and peer) into its private moments buffer.  No compaction, no host-side count, no
+// host-launched collective.
+__global__ void moments_gather_kernel(CommView c, int P, const int32_t* __restrict__ radii, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P || !(radii[i] > 0)) return;
+  float4 acc[3] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
+  for (int r = 0; r < c.world; r++) {
+    const float4* src = reinterpret_cast<const float4*>(c.seg[r] + kCommHeapOff) + 3 * (size_t)i;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      const float4 v = __ldcv(src + k);  // written by another GPU since the last read: never from a cached line
+      acc[k].x += v.x; acc[k].y += v.y; acc[k].z += v.z; acc[k].w += v.w;
+    }
+  }
+  float4* dst = reinterpret_cast<float4*>(out) + 3 * (size_t)i;
+  dst[0] = acc[0]; dst[1] = acc[1]; dst[2] = acc[2];
+}
+
+gsicp_comm* g_raster_comm = nullptr;  // set by gsicp_raster_set_comm; also read by the forward pass (raster_forward.cu)
+
+// Where this rank's render moments accumulate: the exchange segment in a sharded run, else the geometry buffer.
+float* raster_moment_accumulator(const gsicp_raster_args* args, float* geom_moments) {
+  gsicp_comm* c = g_raster_comm;
+  if (!c || c->world <= 1 || args->tile_shard_count <= 1) return geom_moments;
+  return reinterpret_cast<float*>(c->local + kCommHeapOff);
+}
+
 struct BwdShared {
   std::mutex mu;
   gsicp_allreduce_f32_fn fn = nullptr;
@@ -699,6 +733,16 @@ extern "C" int gsicp_raster_set_allreduce(gsicp_allreduce_f32_fn fn, void* user)
 
 // The render moments live in the geometry buffer the forward pass allocated (GeomState::moments, zeroed for the visible
 // Gaussians by preprocess): the backward needs no caller-provided work buffer any more.  Kept for ABI stability.
+extern "C" int gsicp_raster_set_comm(gsicp_comm* comm) {
+  if (comm && !comm->connected) {
+    set_error("gsicp_raster_set_comm: the exchange group is not connected");
+    return GSICP_ESTATE;
+  }
+  std::lock_guard<std::mutex> lock(g_bwd.mu);
+  g_raster_comm = comm;
+  return GSICP_OK;
+}
+
 extern "C" size_t gsicp_raster_backward_work_bytes(int P) { (void)P; return 0; }
 
 extern "C" int gsicp_raster_backward(const gsicp_raster_args* args, int num_rendered, const int32_t* d_radii,
@@ -727,7 +771,13 @@ extern "C" int gsicp_raster_backward(const gsicp_raster_args* args, int num_rend
   GeomState geom = GeomState::from((char*)d_geom, P);
   BinState bin = BinState::from((char*)d_binning, num_rendered);
   ImgState img = ImgState::from((char*)d_image, (size_t)W * H, tiles);
-  float* work = geom.moments;  // [P][12]
+  gsicp_comm* comm = (g_raster_comm && g_raster_comm->world > 1 && shard_count > 1) ? g_raster_comm : nullptr;
+  if (comm && (size_t)P * kG * sizeof(float) > comm->heap_bytes() / 2) {
+    set_error("gsicp_raster_backward: exchange heap too small for %d Gaussians (needs %zu bytes in its lower half)", P,
+              (size_t)P * kG * sizeof(float));
+    return GSICP_ENOMEM;
+  }
+  float* work = raster_moment_accumulator(args, geom.moments);  // [P][12]
 
   if (num_rendered > 0) {
     if (int e = ensure_bwd_smem_attr()) return e;
@@ -744,7 +794,16 @@ extern "C" int gsicp_raster_backward(const gsicp_raster_args* args, int num_rend
     if (args->debug) GSICP_CUDA(cudaStreamSynchronize(stream));
   }
 
-  if (shard_count > 1 && g_bwd.fn) {
+  float* xmom = nullptr;
+  if (comm) {
+    // exchange: barrier (all ranks have finished their render_backward) -> add the world's rows -> barrier (all ranks have
+    // read: the accumulators may be cleared / reused)
+    if (int e = comm_stream_barrier(comm, stream)) return e;
+    GSICP_LAUNCH(moments_gather_kernel, (P + 255) / 256, 256, 0, stream, comm->view(), P, d_radii, geom.moments);
+    if (int e = comm_stream_barrier(comm, stream)) return e;
+    xmom = work;
+    work = geom.moments;
+  } else if (shard_count > 1 && g_bwd.fn) {
     if (int e = allreduce_visible_moments(P, d_radii, work, stream)) return e;
   }
 
@@ -759,7 +818,7 @@ extern "C" int gsicp_raster_backward(const gsicp_raster_args* args, int num_rend
   ba.campos = args->d_campos;
   ProfScope ps_gb(kProfGaussBwd, stream);
   GSICP_LAUNCH(gaussian_backward_kernel, (P + 255) / 256, 256, 0, stream, ba, d_radii, geom.clamped, work, geom.splats, W, H,
-               d_dL_dmeans2D, d_dL_dcolors, d_dL_dopacity, d_dL_dmeans3D, d_dL_dcov3D, d_dL_dsh, d_dL_dscales, d_dL_drotations);
+               d_dL_dmeans2D, d_dL_dcolors, d_dL_dopacity, d_dL_dmeans3D, d_dL_dcov3D, d_dL_dsh, d_dL_dscales, d_dL_drotations, xmom);
   if (args->debug) GSICP_CUDA(cudaStreamSynchronize(stream));
   GSICP_CUDA(cudaGetLastError());
   return GSICP_OK;

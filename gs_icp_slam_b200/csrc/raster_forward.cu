@@ -454,6 +454,8 @@ struct FwdScratch {
 };
 static FwdScratch g_fwd;
 
+float* raster_moment_accumulator(const gsicp_raster_args* args, float* geom_moments);  // raster_backward.cu
+
 int g_render_cull = 1;  // test hook: 0 renders without sub-tile culling (must give identical output)
 
 }  // namespace gsicp
@@ -533,8 +535,10 @@ extern "C" int gsicp_raster_forward(const gsicp_raster_args* args, float* d_out_
     pa.prefiltered = args->prefiltered; pa.shard_count = shard_count; pa.shard_index = shard_index;
     {
       ProfScope ps(kProfPreprocess, stream);
-      GSICP_LAUNCH(preprocess_kernel, (P + 255) / 256, 256, 0, stream, pa, d_radii, d_is_used, geom.splats, geom.moments,
-                   geom.clamped, tiles_touched, tile_count);
+      // the rows preprocess zeroes are where render_backward will accumulate: the geometry buffer, or this rank's exchange
+      // segment in a sharded run (comm.cuh)
+      GSICP_LAUNCH(preprocess_kernel, (P + 255) / 256, 256, 0, stream, pa, d_radii, d_is_used, geom.splats,
+                   raster_moment_accumulator(args, geom.moments), geom.clamped, tiles_touched, tile_count);
     }
     if (args->debug) GSICP_CUDA(cudaStreamSynchronize(stream));
 

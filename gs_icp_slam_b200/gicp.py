@@ -231,6 +231,11 @@ class FastGICP:
     def set_stream(self, cuda_stream):
         check(lib.gsicp_gicp_set_stream(self._h, int(cuda_stream)))
 
+    def set_comm(self, comm):
+        """Multi-GPU: shard the source points (k-NN covariances and LM loop) over the library's exchange group and exchange
+        the normal equations inside the kernels (gs_icp_slam_b200.sharding.ShardGroup); None = single GPU."""
+        check(lib.gsicp_gicp_set_comm(self._h, comm))
+
     def set_host_lm(self, on):
         """Test / A-B hook: drive the LM loop from the host instead of the device-resident kernel (same results)."""
         check(lib.gsicp_gicp_set_host_lm(self._h, int(bool(on))))

@@ -50,6 +50,12 @@ def set_allreduce(fn):
     check(lib.gsicp_raster_set_allreduce(_allreduce_cb, None))
 
 
+def set_comm(comm):
+    """Multi-GPU: the library's own exchange group (gs_icp_slam_b200.sharding.ShardGroup) or None.  With tile sharding
+    active, rasterize_gaussians_backward exchanges the render moments through the peers' device segments inside the call."""
+    check(lib.gsicp_raster_set_comm(comm))
+
+
 def _ptr(t):
     """Device pointer of a tensor, or None for the reference's 'not provided' empty tensor."""
     if t is None or t.numel() == 0:

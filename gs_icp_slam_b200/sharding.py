@@ -88,15 +88,56 @@ def make_raster_allreduce(device, group=None):
 
 
 class ShardGroup:
-    """One rank's membership of a sharded run: wires the rasterizer (tile shards + moments exchange) and FastGICP objects
-    (source-point shards + normal-equation exchange) to the collective.  Collective = torch.distributed all-reduce
-    reached through the library's callbacks, ordered on the library's stream (the callbacks receive the stream
-    the kernels were launched on)."""
+    """One rank's membership of a sharded run: wires the rasterizer (tile shards + render-moment exchange) and FastGICP
+    objects (source-point shards for the k-NN covariances and the LM loop + normal-equation exchange) to the exchange layer.
 
-    def __init__(self, device, world, rank, group=None):
+    Preferred transport ("p2p"): the library's own exchange group (csrc/comm.cuh) — every rank allocates a symmetric
+    device segment, the 64-byte CUDA IPC handles travel once through torch.distributed.all_gather_object, and from then on
+    the kernels exchange through the peers' segments over NVLink with device-side flags: no host-launched collective, no
+    Python in the loop.  Fallback ("nccl-callback", used when CUDA IPC is unavailable): torch.distributed all-reduces
+    reached through the library's callbacks, ordered on the library's stream."""
+
+    def __init__(self, device, world, rank, group=None, heap_bytes=256 << 20, transport="auto"):
         self.device, self.world, self.rank, self.group = device, world, rank, group
         self._gicp = []
         self._raster = False
+        self._comm = None
+        self.transport = "nccl-callback"
+        if transport in ("auto", "p2p") and world > 1:
+            try:
+                self._connect(heap_bytes)
+                self.transport = "p2p"
+            except Exception as ex:  # CUDA IPC not permitted in this environment
+                if transport == "p2p":
+                    raise
+                import sys
+
+                print(f"gs_icp_slam_b200.sharding: peer-memory exchange unavailable ({ex}); using the NCCL callbacks", file=sys.stderr)
+
+    def _connect(self, heap_bytes):
+        import ctypes as C
+
+        import torch.distributed as dist
+
+        from ._lib import check, lib
+
+        comm = C.c_void_p()
+        handle = C.create_string_buffer(64)
+        with torch.cuda.device(self.device):
+            check(lib.gsicp_comm_alloc(int(heap_bytes), C.byref(comm), handle), "gsicp_comm_alloc")
+            handles = [None] * self.world
+            dist.all_gather_object(handles, bytes(handle.raw), group=self.group)
+            ok = all(isinstance(h, (bytes, bytearray)) and len(h) == 64 for h in handles)
+            rc = lib.gsicp_comm_connect(comm, self.world, self.rank, b"".join(handles)) if ok else -1
+            # every rank must agree before anybody relies on the peers' segments
+            flag = torch.tensor([1 if rc == 0 else 0], device=self.device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+            if int(flag.item()) != 1:
+                lib.gsicp_comm_destroy(comm)
+                from ._lib import last_error
+
+                raise RuntimeError("gsicp_comm_connect failed on some rank: " + (last_error() if rc != 0 else "peer"))
+        self._comm = comm
 
     def _allreduce(self, typestr):
         import torch.distributed as dist
@@ -114,14 +155,23 @@ class ShardGroup:
         from . import rasterizer
 
         rasterizer.set_tile_shard(self.world, self.rank)
-        rasterizer.set_allreduce(self._allreduce("<f4"))
+        if self._comm is not None:
+            rasterizer.set_comm(self._comm)
+        else:
+            rasterizer.set_allreduce(self._allreduce("<f4"))
         self._raster = True
 
     def attach_gicp(self, reg):
-        reg.set_shard(self.world, self.rank, self._allreduce("<f8"))
+        if self._comm is not None:
+            reg.set_comm(self._comm)
+        else:
+            reg.set_shard(self.world, self.rank, self._allreduce("<f8"))
         self._gicp.append(reg)
 
     def describe(self):
+        if self.transport == "p2p":
+            return ("in-kernel exchange through the peers' device segments (CUDA IPC over NVLink, device-side sequence flags): "
+                    "28-double normal equations inside the LM kernels, [visible][12] render moments inside the rasterizer's backward")
         return "NCCL all-reduce (torch.distributed) of the 28-double normal equations / the [V][12] render moments on the library's stream"
 
     def close(self):
@@ -130,5 +180,19 @@ class ShardGroup:
 
             rasterizer.set_tile_shard(1, 0)
             rasterizer.set_allreduce(None)
+            rasterizer.set_comm(None)
             self._raster = False
+        for reg in self._gicp:
+            try:
+                reg.set_comm(None)
+            except Exception:
+                pass
         self._gicp = []
+        if self._comm is not None:
+            from ._lib import lib
+
+            torch.cuda.synchronize(self.device)
+            if torch.distributed.is_initialized():
+                torch.distributed.barrier(group=self.group)  # nobody unmaps while a peer's kernel may still touch the segment
+            lib.gsicp_comm_destroy(self._comm)
+            self._comm = None
