@@ -273,6 +273,25 @@ int gsicp_mapping_loss_backward(int H, int W, const float* d_image, const float*
                                 int mask_by_depth, const float* d_grad_loss, const void* d_work, float* d_grad_image,
                                 float* d_grad_depth, void* stream);
 
+/* ---- Mapper bookkeeping on the device (scene/gaussian_model.py) ----
+ * gsicp_adam_step: torch.optim.Adam(..., eps=1e-15).step() for up to 8 parameter tensors in ONE launch
+ *   (gaussian_model.py:214-225 builds six groups with their own lr; mp_Mapper.py:248 steps them).  Host arrays of device
+ *   pointers; counts in elements; `step` is the 1-based step number after the increment, like Adam's state["step"].
+ * gsicp_table_compact: boolean-mask row selection (prune_points / _prune_optimizer, gaussian_model.py:409-446) of n_arrays
+ *   row-major arrays sharing one mask: dst[k][j] = src[k][i] for the j-th kept row i.  Returns the kept-row count (>= 0) or
+ *   a negative error; dst buffers must hold `rows` rows.
+ * gsicp_trackable_target: get_trackable_gaussians_tensor (gaussian_model.py:205-215): rows with sigmoid(opacity) > th and
+ *   trackable != 0, compacted as (xyz, normalised rotation xyzw, exp(scaling)) into device buffers of P rows; returns the
+ *   count.  The outputs go to gsicp_gicp_set_input_target_device / set_target_covariances_fromqs_device without a D2H copy. */
+int gsicp_adam_step(int n_tensors, float* const* d_params, const float* const* d_grads, float* const* d_exp_avg,
+                    float* const* d_exp_avg_sq, const size_t* counts, const float* lrs, int step, float beta1, float beta2,
+                    float eps, void* stream);
+long long gsicp_table_compact(int rows, const uint8_t* d_keep, int n_arrays, const void* const* d_src, void* const* d_dst,
+                              const int* row_bytes, void* stream);
+long long gsicp_trackable_target(int P, const float* d_xyz, const float* d_rotation_raw, const float* d_scaling_raw,
+                                 const float* d_opacity_raw, const uint8_t* d_trackable, float opacity_th, float* d_out_xyz,
+                                 float* d_out_rot, float* d_out_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -9,6 +9,7 @@ rm -rf .gpu_snap/$TAG
 mkdir -p .gpu_snap/$TAG
 tar --exclude=./.git --exclude=./gpurun_out --exclude=./.gpu_snap --exclude='__pycache__' --exclude=./.pytest_cache \
     --exclude='*.o' --exclude='./oracle/_ref/obj' --exclude='./oracle/_ref/fast_gicp/obj' -cf - . | tar -xf - -C .gpu_snap/$TAG
-# keep only the two most recent snapshots
-ls -1dt .gpu_snap/*/ | tail -n +3 | xargs -r rm -rf
+touch .gpu_snap/$TAG
+# keep only the two most recent snapshots (never the one just made)
+ls -1dt .gpu_snap/*/ | grep -v "/$TAG/" | tail -n +2 | xargs -r rm -rf
 du -sh .gpu_snap/$TAG
