@@ -120,8 +120,11 @@ _sig("gsicp_gicp_compute_error", i32, [vp, vp, vp])
 _sig("gsicp_gicp_set_shard", i32, [vp, i32, i32, ALLREDUCE_FN, vp])
 _sig("gsicp_gicp_set_stream", i32, [vp, vp])
 _sig("gsicp_gicp_set_host_lm", i32, [vp, i32])
+_sig("gsicp_gicp_set_source_filter_device", i32, [vp, i32, vp, i32])
+_sig("gsicp_gicp_set_target_filter_device", i32, [vp, i32, vp, i32])
 _sig("gsicp_comm_alloc", i32, [C.c_size_t, C.POINTER(vp), vp])
 _sig("gsicp_comm_connect", i32, [vp, i32, i32, vp])
+_sig("gsicp_comm_connect_local", i32, [vp, i32, i32, C.POINTER(vp)])
 _sig("gsicp_comm_destroy", None, [vp])
 _sig("gsicp_comm_world", i32, [vp])
 _sig("gsicp_comm_rank", i32, [vp])

@@ -5,8 +5,14 @@
 #include <vector>
 #include "host_common.h"
 
+#include <cstdlib>
 namespace gsicp {
 std::atomic<uint64_t> g_launches{0};
+int g_debug_sync = [] { const char* e = std::getenv("GSICP_DEBUG_SYNC"); return (e && e[0] == '1') ? 1 : 0; }();
+void debug_sync_report(const char* kernel, cudaStream_t stream) {
+  const cudaError_t e = cudaStreamSynchronize(stream);
+  if (e != cudaSuccess) fprintf(stderr, "[gsicp debug] kernel %s failed: %s\n", kernel, cudaGetErrorString(e));
+}
 static thread_local char g_err[512] = "";
 
 void set_error(const char* fmt, ...) {

@@ -90,10 +90,26 @@ extern "C" int gsicp_comm_connect(gsicp_comm* c, int world, int rank, const void
   return GSICP_OK;
 }
 
+// Test hook: connect the ranks of a group that live in ONE process on ONE device (CUDA IPC cannot map a process's own
+// allocation): the peers' segments are given as plain device pointers.  Lets a single-GPU box exercise the device-side
+// exchange protocols (two "ranks" on two streams).
+extern "C" int gsicp_comm_connect_local(gsicp_comm* c, int world, int rank, gsicp_comm* const* group) {
+  if (!c || !group || world < 1 || world > kMaxRanks || rank < 0 || rank >= world) return GSICP_EINVAL;
+  c->world = world;
+  c->rank = rank;
+  for (int r = 0; r < world; r++) {
+    if (!group[r] || !group[r]->local) return GSICP_EINVAL;
+    c->peer[r] = group[r]->local;
+  }
+  c->local_only = true;
+  c->connected = true;
+  return GSICP_OK;
+}
+
 extern "C" void gsicp_comm_destroy(gsicp_comm* c) {
   if (!c) return;
   for (int r = 0; r < c->world; r++)
-    if (r != c->rank && c->peer[r]) cudaIpcCloseMemHandle(c->peer[r]);
+    if (!c->local_only && r != c->rank && c->peer[r]) cudaIpcCloseMemHandle(c->peer[r]);
   if (c->local) cudaFree(c->local);
   delete c;
 }

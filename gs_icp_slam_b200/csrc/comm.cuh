@@ -109,6 +109,7 @@ struct gsicp_comm {
   char* local = nullptr;
   char* peer[gsicp::kMaxRanks] = {};
   bool connected = false;
+  bool local_only = false;         // test hook: all ranks in one process (gsicp_comm_connect_local)
   unsigned long long bar_seq = 0;  // stream-barrier sequence (host-side counter; identical call order on every rank)
   unsigned long long lm_seq = 0;   // last LM exchange sequence number handed out (host-side, identical on every rank)
   bool lm_resync = false;          // the last launch consumed a data-dependent number of exchanges: re-align with a barrier

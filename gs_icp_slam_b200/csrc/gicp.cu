@@ -1102,7 +1102,7 @@ int ensure_grid(gsicp_gicp* h, Cloud& c) {
   return GSICP_OK;
 }
 
-int set_filter(gsicp_gicp* h, Cloud& c, int num_trackable, const int32_t* filter, int n) {
+int set_filter(gsicp_gicp* h, Cloud& c, int num_trackable, const int32_t* filter, int n, bool device_src = false) {
   if (n < 0 || num_trackable < 0 || (n > 0 && !filter)) {
     set_error("set_filter: bad arguments");
     return GSICP_EINVAL;
@@ -1112,7 +1112,8 @@ int set_filter(gsicp_gicp* h, Cloud& c, int num_trackable, const int32_t* filter
   if (n == 0) return GSICP_OK;
   if (int e = c.filter.ensure((size_t)n * 4)) return e;
   // pageable source: the runtime stages it before returning, so no pinned staging buffer (and no sync) is needed
-  GSICP_CUDA(cudaMemcpyAsync(c.filter.ptr, filter, (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
+  GSICP_CUDA(cudaMemcpyAsync(c.filter.ptr, filter, (size_t)n * 4, device_src ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
+                             h->stream));
   return GSICP_OK;
 }
 
@@ -1690,6 +1691,8 @@ int gsicp_gicp_set_input_target_device(gsicp_gicp* h, const float* d_xyz, int n)
 }
 int gsicp_gicp_set_source_filter(gsicp_gicp* h, int nt, const int32_t* f, int n) { H_CHECK(h); return set_filter(h, h->src, nt, f, n); }
 int gsicp_gicp_set_target_filter(gsicp_gicp* h, int nt, const int32_t* f, int n) { H_CHECK(h); return set_filter(h, h->tgt, nt, f, n); }
+int gsicp_gicp_set_source_filter_device(gsicp_gicp* h, int nt, const int32_t* f, int n) { H_CHECK(h); return set_filter(h, h->src, nt, f, n, true); }
+int gsicp_gicp_set_target_filter_device(gsicp_gicp* h, int nt, const int32_t* f, int n) { H_CHECK(h); return set_filter(h, h->tgt, nt, f, n, true); }
 
 int gsicp_gicp_calculate_target_covariance_with_filter(gsicp_gicp* h) { H_CHECK(h); return compute_covariances(h, h->tgt, true, false); }
 int gsicp_gicp_calculate_source_covariance(gsicp_gicp* h) { H_CHECK(h); return compute_covariances(h, h->src, false, true); }

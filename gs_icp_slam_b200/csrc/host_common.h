@@ -12,11 +12,15 @@ namespace gsicp {
 extern std::atomic<uint64_t> g_launches;
 void set_error(const char* fmt, ...);
 
-// Counts every kernel launch of ours; bench.py reports it as gpu_launches.
+// Counts every kernel launch of ours; bench.py reports it as gpu_launches.  With GSICP_DEBUG_SYNC=1 in the environment every
+// launch is followed by a stream synchronize and the first failing kernel is named on stderr (debugging aid only).
+extern int g_debug_sync;
+void debug_sync_report(const char* kernel, cudaStream_t stream);
 #define GSICP_LAUNCH(kernel, grid, block, smem, stream, ...)          \
   do {                                                                \
     kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);       \
     ::gsicp::g_launches.fetch_add(1, std::memory_order_relaxed);      \
+    if (::gsicp::g_debug_sync) ::gsicp::debug_sync_report(#kernel, (stream)); \
   } while (0)
 
 #define GSICP_CUDA(expr)                                                                  \

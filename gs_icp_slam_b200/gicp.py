@@ -86,10 +86,22 @@ class FastGICP:
             check(lib.gsicp_gicp_set_input_target(self._h, a.ctypes.data, a.shape[0], f32))
 
     def set_source_filter(self, num_trackable, input_filter):
+        if hasattr(input_filter, "is_cuda") and input_filter.is_cuda:  # zero-copy path
+            import torch
+
+            t = input_filter.detach().to(torch.int32).contiguous().view(-1)
+            check(lib.gsicp_gicp_set_source_filter_device(self._h, int(num_trackable), t.data_ptr(), t.shape[0]))
+            return
         f = np.ascontiguousarray(np.asarray(input_filter).reshape(-1), dtype=np.int32)
         check(lib.gsicp_gicp_set_source_filter(self._h, int(num_trackable), f.ctypes.data, f.shape[0]))
 
     def set_target_filter(self, num_trackable, input_filter):
+        if hasattr(input_filter, "is_cuda") and input_filter.is_cuda:
+            import torch
+
+            t = input_filter.detach().to(torch.int32).contiguous().view(-1)
+            check(lib.gsicp_gicp_set_target_filter_device(self._h, int(num_trackable), t.data_ptr(), t.shape[0]))
+            return
         f = np.ascontiguousarray(np.asarray(input_filter).reshape(-1), dtype=np.int32)
         check(lib.gsicp_gicp_set_target_filter(self._h, int(num_trackable), f.ctypes.data, f.shape[0]))
 

@@ -17,14 +17,13 @@ import torch
 
 from ._lib import check, lib
 
+from ._lib import _sig  # noqa: E402  (registers the bindings: tests/test_abi.py checks that every declared symbol is bound)
+
 _vp = C.c_void_p
-lib.gsicp_adam_step.restype = C.c_int
-lib.gsicp_adam_step.argtypes = [C.c_int, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(C.c_size_t),
-                                C.POINTER(C.c_float), C.c_int, C.c_float, C.c_float, C.c_float, _vp]
-lib.gsicp_table_compact.restype = C.c_longlong
-lib.gsicp_table_compact.argtypes = [C.c_int, _vp, C.c_int, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(C.c_int), _vp]
-lib.gsicp_trackable_target.restype = C.c_longlong
-lib.gsicp_trackable_target.argtypes = [C.c_int, _vp, _vp, _vp, _vp, _vp, C.c_float, _vp, _vp, _vp, _vp]
+_sig("gsicp_adam_step", C.c_int, [C.c_int, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(C.c_size_t),
+                                  C.POINTER(C.c_float), C.c_int, C.c_float, C.c_float, C.c_float, _vp])
+_sig("gsicp_table_compact", C.c_longlong, [C.c_int, _vp, C.c_int, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(C.c_int), _vp])
+_sig("gsicp_trackable_target", C.c_longlong, [C.c_int, _vp, _vp, _vp, _vp, _vp, C.c_float, _vp, _vp, _vp, _vp])
 
 MAX_TENSORS_PER_LAUNCH = 8
 

@@ -241,3 +241,35 @@ def trackable_filter(n_points, trackable):
     f = np.zeros(n_points, dtype=np.int32)
     f[trackable] = np.arange(1, len(trackable) + 1, dtype=np.int32)
     return f
+
+
+def write_dataset(path, n_frames, cam=None, n_traj=200):
+    """Write the synthetic RGB-D sequence to disk in the reference's Replica layout (mp_Tracker.py:341-352,
+    utils/traj_utils.py:38-50): images/frameNNNNNN.jpg, depth_images/depthNNNNNN.png (uint16, depth * depth_scale),
+    traj.txt (one flattened camera-to-world 4x4 per line) and caminfo.txt (configs/*/caminfo.txt format).
+    Returns the path of the camera file."""
+    import os
+
+    import cv2
+
+    cam = dict(TUM if cam is None else cam)
+    os.makedirs(os.path.join(path, "images"), exist_ok=True)
+    os.makedirs(os.path.join(path, "depth_images"), exist_ok=True)
+    poses = []
+    for i in range(n_frames):
+        c2w = trajectory_pose(i, n_traj)
+        depth, hit = raycast_depth(c2w, cam)
+        rgb = texture(hit).reshape(cam["H"], cam["W"], 3)
+        img = np.clip(np.round(rgb * 255.0), 0, 255).astype(np.uint8)
+        cv2.imwrite(os.path.join(path, "images", f"frame{i:06d}.jpg"), img, [cv2.IMWRITE_JPEG_QUALITY, 95])
+        d16 = np.clip(np.round(depth * cam["depth_scale"]), 0, 65535).astype(np.uint16)
+        cv2.imwrite(os.path.join(path, "depth_images", f"depth{i:06d}.png"), d16)
+        poses.append(c2w)
+    with open(os.path.join(path, "traj.txt"), "w") as f:
+        for p in poses:
+            f.write(" ".join(f"{v:.12e}" for v in p.reshape(-1)) + "\n")
+    cfg = os.path.join(path, "caminfo.txt")
+    with open(cfg, "w") as f:
+        f.write("## camera parameters\nW H fx fy cx cy depth_scale depth_trunc dataset_type\n")
+        f.write(f"{cam['W']} {cam['H']} {cam['fx']} {cam['fy']} {cam['cx']} {cam['cy']} {cam['depth_scale']} {cam['depth_trunc']} replica")
+    return cfg

@@ -238,6 +238,8 @@ typedef struct gsicp_comm gsicp_comm;
 int gsicp_comm_alloc(size_t heap_bytes, gsicp_comm** out, void* handle64);
 int gsicp_comm_connect(gsicp_comm*, int world, int rank, const void* handles /* world x 64 bytes, rank order */);
 void gsicp_comm_destroy(gsicp_comm*);
+/* Test hook: all ranks of the group live in this process on one device (plain device pointers instead of IPC handles). */
+int gsicp_comm_connect_local(gsicp_comm*, int world, int rank, gsicp_comm* const* group);
 int gsicp_comm_world(const gsicp_comm*);
 int gsicp_comm_rank(const gsicp_comm*);
 int gsicp_comm_barrier(gsicp_comm*, void* stream);   /* stream-ordered barrier over the group */
@@ -291,6 +293,27 @@ long long gsicp_table_compact(int rows, const uint8_t* d_keep, int n_arrays, con
 long long gsicp_trackable_target(int P, const float* d_xyz, const float* d_rotation_raw, const float* d_scaling_raw,
                                  const float* d_opacity_raw, const uint8_t* d_trackable, float opacity_th, float* d_out_xyz,
                                  float* d_out_rot, float* d_out_scale, void* stream);
+
+/* ---- Tracker front-end on the device (mp_Tracker.py:394-431, 229, 256-274, 374-392) ----
+ * gsicp_frontend_cloud: set_downsample_filter + downsample_and_make_pointcloud2: depth uint16 [H,W] and rgb uint8 [H,W,3]
+ *   (device) -> camera-frame points [n,3], colours [n,3] (/255), z [n] of the sampled pixels with depth != 0 in raster
+ *   order, the 1-based trackable filter [n] pygicp's set_source_filter takes (0 = z > depth_trunc) and the indices of the
+ *   trackable points [n_trackable].  Output buffers hold gsicp_frontend_max_points(W, H, step) rows.
+ * gsicp_frontend_keyframe: points to the world frame (R p - R T with R, T as mp_Tracker.py:224-229 forms them) and
+ *   q_cam (x) rots (quaternion_multiply, xyzw); d_rots may be NULL.
+ * gsicp_frontend_not_overlapped: eliminate_overlapped2 + the filter update (mp_Tracker.py:267-269): trackable indices whose
+ *   squared NN distance exceeds the threshold, compacted. */
+int gsicp_frontend_max_points(int W, int H, int step);
+int gsicp_frontend_cloud(const uint16_t* d_depth, const uint8_t* d_rgb, int W, int H, int step, float fx, float fy, float cx,
+                         float cy, float depth_scale, float depth_trunc, float* d_points, float* d_colors, float* d_z,
+                         int32_t* d_filter, int32_t* d_trackable, int* n_points, int* n_trackable, void* stream);
+int gsicp_frontend_keyframe(int n, const float* d_points_cam, const float* d_rots, const float R[9], const float T[3],
+                            const float q_xyzw[4], float* d_points_world, float* d_rots_world, void* stream);
+int gsicp_frontend_not_overlapped(int n_trackable, const float* d_sq_dist, float threshold, const int32_t* d_trackable,
+                                  int32_t* d_out, int* n_out, void* stream);
+/* Device-resident filters for the zero-copy tracker path (N1): like gsicp_gicp_set_source/target_filter with device pointers. */
+int gsicp_gicp_set_source_filter_device(gsicp_gicp*, int num_trackable, const int32_t* d_filter, int n);
+int gsicp_gicp_set_target_filter_device(gsicp_gicp*, int num_trackable, const int32_t* d_filter, int n);
 
 #ifdef __cplusplus
 }

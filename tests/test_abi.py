@@ -18,6 +18,7 @@ def _header_symbols():
 
 def test_library_exports_every_declared_symbol():
     from gs_icp_slam_b200 import _lib
+    from gs_icp_slam_b200 import frontend, map_table  # noqa: F401  (bind their entry points)
 
     out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True, check=True).stdout
     exported = set(re.findall(r"\sT\s+(gsicp_\w+)", out))
