@@ -443,16 +443,19 @@ __global__ void copy_ranges_kernel(int tiles, const uint2* __restrict__ ranges, 
   }
 }
 
-// Library-internal scratch (not needed by backward).  One rasterization in flight per process,
-// like the reference (which launches everything on the legacy default stream).
+// Library-internal scratch (not needed by backward), one set PER DEVICE: one rasterization in flight per device (the mutex
+// is held until the forward's launches are enqueued; streams of one device share the scratch and are serialised by the
+// host-side wait on the instance count).  The reference launches everything on the legacy default stream.
+constexpr int kMaxDevices = 32;
 struct FwdScratch {
   std::mutex mu;
   Scratch per_gaussian, per_instance, cub_tmp;
   unsigned long long* h_map = nullptr;  // mapped pinned: [0] = num_rendered, [1] = sequence word, [2] = largest tile
   unsigned long long* d_map = nullptr;
   unsigned long long seq = 0;
+  bool sort_attr_set = false;  // cudaFuncSetAttribute of the big tile sort, per device
 };
-static FwdScratch g_fwd;
+static FwdScratch g_fwd_dev[kMaxDevices];
 
 float* raster_moment_accumulator(const gsicp_raster_args* args, float* geom_moments);  // raster_backward.cu
 
@@ -499,6 +502,13 @@ extern "C" int gsicp_raster_forward(const gsicp_raster_args* args, float* d_out_
   GeomState geom = GeomState::from(geom_p, P);
   ImgState img = ImgState::from(img_p, N, tiles);
 
+  int dev = 0;
+  GSICP_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= kMaxDevices) {
+    set_error("gsicp_raster_forward: device index %d out of range", dev);
+    return GSICP_EINVAL;
+  }
+  FwdScratch& g_fwd = g_fwd_dev[dev];
   std::lock_guard<std::mutex> lock(g_fwd.mu);
   if (!g_fwd.h_map) {
     GSICP_CUDA(cudaHostAlloc((void**)&g_fwd.h_map, 4 * sizeof(unsigned long long), cudaHostAllocMapped));
@@ -604,7 +614,7 @@ extern "C" int gsicp_raster_forward(const gsicp_raster_args* args, float* d_out_
       ProfScope ps(kProfTileSort, stream);
       if (!big) {
         if (n_big > 0) {
-          static bool attr_set = false;
+          bool& attr_set = g_fwd.sort_attr_set;
           if (!attr_set) {
             GSICP_CUDA(cudaFuncSetAttribute(tile_sort_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSortCap * 8));
             attr_set = true;

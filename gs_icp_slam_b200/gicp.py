@@ -25,6 +25,24 @@ class FastGICP:
         self._h = lib.gsicp_gicp_create()
         if not self._h:
             raise _lib.GsicpError("gsicp_gicp_create failed: " + _lib.last_error())
+        self._stream_ptr = 0  # the handle's stream (0 = legacy default stream)
+
+    def _device_input(self, t):
+        """float32 contiguous view of a CUDA tensor, ordered for the handle's stream: the library enqueues an asynchronous
+        copy on ITS stream, so that stream first waits for the work torch has queued on the tensor's producer stream, and the
+        caching allocator is told the block is in use there (a conversion temporary dies when this call returns)."""
+        import torch
+
+        x = t.detach()
+        if x.dtype is not torch.float32 or not x.is_contiguous():
+            x = x.float().contiguous()
+        cur = torch.cuda.current_stream(x.device)
+        if cur.cuda_stream != self._stream_ptr:
+            ext = torch.cuda.ExternalStream(self._stream_ptr, device=x.device) if self._stream_ptr else torch.cuda.default_stream(x.device)
+            if ext.cuda_stream != cur.cuda_stream:
+                ext.wait_stream(cur)
+                x.record_stream(ext)
+        return x
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
@@ -72,7 +90,7 @@ class FastGICP:
     def set_input_source(self, points):
         a, f32 = self._cloud(points)
         if f32 is None:
-            t = a.detach().float().contiguous()
+            t = self._device_input(a)
             check(lib.gsicp_gicp_set_input_source_device(self._h, t.data_ptr(), t.shape[0]))
         else:
             check(lib.gsicp_gicp_set_input_source(self._h, a.ctypes.data, a.shape[0], f32))
@@ -80,7 +98,7 @@ class FastGICP:
     def set_input_target(self, points):
         a, f32 = self._cloud(points)
         if f32 is None:
-            t = a.detach().float().contiguous()
+            t = self._device_input(a)
             check(lib.gsicp_gicp_set_input_target_device(self._h, t.data_ptr(), t.shape[0]))
         else:
             check(lib.gsicp_gicp_set_input_target(self._h, a.ctypes.data, a.shape[0], f32))
@@ -131,8 +149,8 @@ class FastGICP:
 
     def _fromqs(self, fn, rotationsq, scales):
         if hasattr(rotationsq, "is_cuda") and rotationsq.is_cuda:  # zero-copy path for CUDA tensors
-            r = rotationsq.detach().float().contiguous().view(-1)
-            s = scales.detach().float().contiguous().view(-1)
+            r = self._device_input(rotationsq).view(-1)
+            s = self._device_input(scales).view(-1)
             if r.numel() // 4 != s.numel() // 3:
                 print("qs size not matched", file=sys.stderr)
                 return
@@ -242,6 +260,7 @@ class FastGICP:
 
     def set_stream(self, cuda_stream):
         check(lib.gsicp_gicp_set_stream(self._h, int(cuda_stream)))
+        self._stream_ptr = int(cuda_stream)
 
     def set_comm(self, comm):
         """Multi-GPU: shard the source points (k-NN covariances and LM loop) over the library's exchange group and exchange
