@@ -1534,7 +1534,7 @@ int run_align_device(gsicp_gicp* h, Iso& x0) {
   GSICP_CUDA(cudaMemsetAsync(h->lm_barrier.ptr, 0, sizeof(unsigned int), h->stream));
   if (end > begin)
     if (int e = ensure_grid(h, h->tgt)) return e;
-  LmArgs a;
+  LmArgs a = {};
   a.tgt = h->tgt.grid.view();
   a.begin = begin; a.end = end;
   a.max_corr_sq = h->max_corr * h->max_corr;
@@ -1551,6 +1551,11 @@ int run_align_device(gsicp_gicp* h, Iso& x0) {
     const unsigned long long bound = (unsigned long long)std::max(1, h->max_iterations) * (unsigned long long)(1 + std::max(1, h->lm_max_iterations));
     if (int e = comm_take_seq(h, bound + 1, &a.xseq)) return e;
   }
+  a.max_iterations = h->max_iterations; a.lm_max_iterations = h->lm_max_iterations;
+  a.rot_eps = h->rot_eps; a.trans_eps = h->trans_eps; a.init_lambda_factor = h->lm_init_lambda_factor;
+  a.guess = x0;
+  a.result = h->d_lm;
+  a.seq = ++h->seq;
   {
     ProfScope ps(kProfLinearize, h->stream);  // slot "gicp_linearize": the whole device-resident LM loop
     GSICP_LAUNCH(align_lm_kernel, blocks, kLmBlock, 0, h->stream, a);

@@ -33,11 +33,13 @@ constexpr int kRow = 36;  // words per staged row: 32 pixels + 4 pad (conflict-f
 constexpr int kWarps = kTilePixels / 32;
 
 // Dynamic shared memory of render_backward_kernel (59 392 B; three CTAs per SM):
-struct __align__(16) BwdSmem {
-  float4 a[2][kTilePixels], b[2][kTilePixels], c[2][kTilePixels];  // double-buffered staging of 256 splat records
+template <int kStage>
+struct __align__(16) BwdSmemT {
+  float4 a[2][kStage], b[2][kStage], c[2][kStage];  // double-buffered staging of kStage splat records
   float tq[kWarps][kGrp * kRow], wq[kWarps][kGrp * kRow];          // per-warp transposition buffers of the MMA reduction
   float4 aw[kWarps][4][32];                                        // per-warp constant A fragments of the w-block
 };
+using BwdSmem = BwdSmemT<kTilePixels>;
 
 // D += A * B, A 16x8 (row major), B 8x8 (column major), tf32 inputs (the low 13 mantissa bits are ignored), fp32 accumulate.
 // Fragment layout (PTX ISA, mma.m16n8k8 .tf32), g = lane >> 2, t = lane & 3:
@@ -61,8 +63,10 @@ __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__flo
 // Measured and dropped (profiles/r2b_notes.md): a software-pipelined survivor loop (alpha evaluation of candidate k+1
 // interleaved with the blend chain of candidate k in one predicated basic block: 240 us vs 226 us) and a 128-register /
 // 2-CTA-per-SM build (262-276 us): the kernel wants resident warps, not more ILP per warp.
-template <bool kCull>
-__global__ void __launch_bounds__(kTilePixels, 3)
+// kStage / kMinBlocks: (256, 3) = 80 registers, 58 KB of shared memory, 3 CTAs per SM (default);
+// (128, 4) = 64 registers, 46 KB, 4 CTAs per SM (experiment: GSICP_BWD_VARIANT=1).
+template <bool kCull, int kStage = kTilePixels, int kMinBlocks = 3>
+__global__ void __launch_bounds__(kTilePixels, kMinBlocks)
 render_backward_kernel(const uint32_t* __restrict__ tile_order, const uint2* __restrict__ ranges,
                        const uint32_t* __restrict__ point_list, int W, int H,
                        int tiles_x, const float* __restrict__ bg, const Splat* __restrict__ splats,
@@ -81,7 +85,7 @@ render_backward_kernel(const uint32_t* __restrict__ tile_order, const uint2* __r
   const int pix = py * W + px;
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  BwdSmem& sm = *reinterpret_cast<BwdSmem*>(smem_raw);
+  BwdSmemT<kStage>& sm = *reinterpret_cast<BwdSmemT<kStage>*>(smem_raw);
 
   const uint2 range = ranges[tile];
   const int total = (int)(range.y - range.x);
@@ -207,7 +211,7 @@ render_backward_kernel(const uint32_t* __restrict__ tile_order, const uint2* __r
   // Back to front: batch `base` covers list positions [total-base-n, total-base), staged reversed
   // (slot k = position total-base-1-k) like backward.cu:519-531.
   auto stage = [&](int base, int buf) {
-    const int n = min(kTilePixels, total - base);
+    const int n = min(kStage, total - base);
     if (tid < n) {
       const Splat* sp = splats + point_list[range.y - 1 - base - tid];
       cp_async16(&sm.a[buf][tid], &sp->a);
@@ -218,11 +222,11 @@ render_backward_kernel(const uint32_t* __restrict__ tile_order, const uint2* __r
   };
   if (total > 0) stage(0, 0);
 
-  for (int base = 0, buf = 0; base < total; base += kTilePixels, buf ^= 1) {
-    const int n = min(kTilePixels, total - base);
+  for (int base = 0, buf = 0; base < total; base += kStage, buf ^= 1) {
+    const int n = min(kStage, total - base);
     cp_async_wait_all();
     __syncthreads();  // batch `base` is staged; every warp has finished reading the other buffer
-    if (base + kTilePixels < total) stage(base + kTilePixels, buf ^ 1);
+    if (base + kStage < total) stage(base + kStage, buf ^ 1);
 
     const int first_pos = total - base;  // 1-based contributor id of slot 0
     if (first_pos - (n - 1) > warp_last) continue;  // the whole batch lies behind this warp's last contributor
@@ -584,6 +588,7 @@ gaussian_backward_kernel(BwdArgs a, const int32_t* __restrict__ radii, const uin
 }
 
 extern int g_render_cull;
+int g_bwd_variant = [] { const char* e = getenv("GSICP_BWD_VARIANT"); return e ? atoi(e) : 0; }();
 
 // ---- multi-GPU: all-reduce of the render moments of the VISIBLE Gaussians ----
 // Every rank preprocesses all Gaussians, so the set {radii > 0} and its index order are identical on all ranks: the
@@ -720,6 +725,8 @@ static int ensure_bwd_smem_attr() {
   if (dev < 0 || dev >= 64 || done[dev]) return GSICP_OK;
   GSICP_CUDA(cudaFuncSetAttribute(render_backward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BwdSmem)));
   GSICP_CUDA(cudaFuncSetAttribute(render_backward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BwdSmem)));
+  GSICP_CUDA(cudaFuncSetAttribute((render_backward_kernel<true, 128, 4>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)sizeof(BwdSmemT<128>)));
   done[dev] = true;
   return GSICP_OK;
 }
@@ -782,12 +789,16 @@ extern "C" int gsicp_raster_backward(const gsicp_raster_args* args, int num_rend
   if (num_rendered > 0) {
     if (int e = ensure_bwd_smem_attr()) return e;
     ProfScope ps(kProfRenderBwd, stream);
-    if (g_render_cull) {
-      GSICP_LAUNCH(render_backward_kernel<true>, tiles, kTilePixels, sizeof(BwdSmem), stream, img.tile_order, img.ranges, bin.point_list,
+    if (!g_render_cull) {  // test hook: no sub-tile culling
+      GSICP_LAUNCH(render_backward_kernel<false>, tiles, kTilePixels, sizeof(BwdSmem), stream, img.tile_order, img.ranges, bin.point_list,
                    W, H, tiles_x, args->d_background, geom.splats, img.final_T, img.n_contrib, d_dL_dout_color, d_dL_dout_depth,
                    work, shard_count, shard_index);
-    } else {  // test hook: no sub-tile culling
-      GSICP_LAUNCH(render_backward_kernel<false>, tiles, kTilePixels, sizeof(BwdSmem), stream, img.tile_order, img.ranges, bin.point_list,
+    } else if (g_bwd_variant == 1) {
+      GSICP_LAUNCH((render_backward_kernel<true, 128, 4>), tiles, kTilePixels, sizeof(BwdSmemT<128>), stream, img.tile_order, img.ranges,
+                   bin.point_list, W, H, tiles_x, args->d_background, geom.splats, img.final_T, img.n_contrib, d_dL_dout_color,
+                   d_dL_dout_depth, work, shard_count, shard_index);
+    } else {
+      GSICP_LAUNCH(render_backward_kernel<true>, tiles, kTilePixels, sizeof(BwdSmem), stream, img.tile_order, img.ranges, bin.point_list,
                    W, H, tiles_x, args->d_background, geom.splats, img.final_T, img.n_contrib, d_dL_dout_color, d_dL_dout_depth,
                    work, shard_count, shard_index);
     }
@@ -823,3 +834,5 @@ extern "C" int gsicp_raster_backward(const gsicp_raster_args* args, int num_rend
   GSICP_CUDA(cudaGetLastError());
   return GSICP_OK;
 }
+
+extern "C" void gsicp_test_set_bwd_variant(int v) { gsicp::g_bwd_variant = v; }

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     assert len(declared) >= 45
     missing = [s for s in declared if s not in exported]
     assert not missing, f"declared in include/gsicp_b200.h but not exported: {missing}"
-    assert set(declared) <= set(_lib.BOUND) | {"gsicp_test_set_render_cull"}
+    assert set(declared) <= set(_lib.BOUND) | {"gsicp_test_set_render_cull", "gsicp_test_set_bwd_variant"}
     assert b"sm_100a" in _lib.lib.gsicp_build_info()
 
 
