@@ -30,7 +30,7 @@ struct AdamTensors {
 };
 
 __global__ void __launch_bounds__(256)
-adam_kernel(AdamTensors t, unsigned long long total, float beta1, float beta2, float bc2_sqrt_inv, float eps) {
+adam_kernel(AdamTensors t, unsigned long long total, float w1, float beta2, float w2, float bc2_sqrt_inv, float eps) {
   for (unsigned long long idx = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (unsigned long long)gridDim.x * blockDim.x) {
     int k = 0;
@@ -40,8 +40,9 @@ adam_kernel(AdamTensors t, unsigned long long total, float beta1, float beta2, f
     const unsigned long long i = idx - (k > 0 ? t.end[k - 1] : 0ull);
     const float g = t.g[k][i];
     float m = t.m[k][i], v = t.v[k][i];
-    m = m + (1.0f - beta1) * (g - m);              // exp_avg.lerp_(grad, 1 - beta1)
-    v = v * beta2 + (1.0f - beta2) * g * g;        // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1 - beta2)
+    // w1 = float(1 - beta1), w2 = float(1 - beta2) are formed in double on the host and rounded once, as PyTorch passes them
+    m = m + w1 * (g - m);                          // exp_avg.lerp_(grad, 1 - beta1)
+    v = v * beta2 + w2 * g * g;                    // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1 - beta2)
     const float denom = sqrtf(v) * bc2_sqrt_inv + eps;
     t.p[k][i] = t.p[k][i] - t.step_size[k] * (m / denom);
     t.m[k][i] = m;
@@ -180,8 +181,8 @@ static int table_wait_count(unsigned long long seq, cudaStream_t stream, long lo
 using namespace gsicp;
 
 extern "C" int gsicp_adam_step(int n_tensors, float* const* d_params, const float* const* d_grads, float* const* d_exp_avg,
-                               float* const* d_exp_avg_sq, const size_t* counts, const float* lrs, int step, float beta1,
-                               float beta2, float eps, void* stream_v) {
+                               float* const* d_exp_avg_sq, const size_t* counts, const float* lrs, int step, double beta1,
+                               double beta2, double eps, void* stream_v) {
   if (n_tensors < 0 || n_tensors > kAdamMaxTensors || step < 1) {
     set_error("gsicp_adam_step: %d tensors (max %d), step %d", n_tensors, kAdamMaxTensors, step);
     return GSICP_EINVAL;
@@ -189,8 +190,8 @@ extern "C" int gsicp_adam_step(int n_tensors, float* const* d_params, const floa
   AdamTensors t;
   t.n = 0;
   unsigned long long total = 0;
-  const double bc1 = 1.0 - std::pow((double)beta1, (double)step);
-  const double bc2_sqrt = std::sqrt(1.0 - std::pow((double)beta2, (double)step));
+  const double bc1 = 1.0 - std::pow(beta1, (double)step);
+  const double bc2_sqrt = std::sqrt(1.0 - std::pow(beta2, (double)step));
   for (int k = 0; k < n_tensors; k++) {
     if (counts[k] == 0) continue;
     if (!d_params[k] || !d_grads[k] || !d_exp_avg[k] || !d_exp_avg_sq[k]) {
@@ -205,7 +206,8 @@ extern "C" int gsicp_adam_step(int n_tensors, float* const* d_params, const floa
   }
   if (total == 0) return GSICP_OK;
   const int blocks = (int)std::min<unsigned long long>((total + 255) / 256, 148ull * 16);
-  GSICP_LAUNCH(adam_kernel, blocks, 256, 0, (cudaStream_t)stream_v, t, total, beta1, beta2, (float)(1.0 / bc2_sqrt), eps);
+  GSICP_LAUNCH(adam_kernel, blocks, 256, 0, (cudaStream_t)stream_v, t, total, (float)(1.0 - beta1), (float)beta2,
+               (float)(1.0 - beta2), (float)(1.0 / bc2_sqrt), (float)eps);
   GSICP_CUDA(cudaGetLastError());
   return GSICP_OK;
 }

@@ -588,7 +588,9 @@ gaussian_backward_kernel(BwdArgs a, const int32_t* __restrict__ radii, const uin
 }
 
 extern int g_render_cull;
-int g_bwd_variant = [] { const char* e = getenv("GSICP_BWD_VARIANT"); return e ? atoi(e) : 0; }();
+// 1 (default): 128-entry staging, 64 registers, 4 CTAs/SM; 0: 256-entry staging, 3 CTAs/SM (r2e: 222.5 vs 227.0 us at C3,
+// 1103 vs 1203 us at C4).  Same arithmetic per survivor; the switch exists for tools/bench_raster.py and the parity tests.
+int g_bwd_variant = [] { const char* e = getenv("GSICP_BWD_VARIANT"); return e ? atoi(e) : 1; }();
 
 // ---- multi-GPU: all-reduce of the render moments of the VISIBLE Gaussians ----
 // Every rank preprocesses all Gaussians, so the set {radii > 0} and its index order are identical on all ranks: the

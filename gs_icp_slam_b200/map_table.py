@@ -21,7 +21,7 @@ from ._lib import _sig  # noqa: E402  (registers the bindings: tests/test_abi.py
 
 _vp = C.c_void_p
 _sig("gsicp_adam_step", C.c_int, [C.c_int, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(C.c_size_t),
-                                  C.POINTER(C.c_float), C.c_int, C.c_float, C.c_float, C.c_float, _vp])
+                                  C.POINTER(C.c_float), C.c_int, C.c_double, C.c_double, C.c_double, _vp])
 _sig("gsicp_table_compact", C.c_longlong, [C.c_int, _vp, C.c_int, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(C.c_int), _vp])
 _sig("gsicp_trackable_target", C.c_longlong, [C.c_int, _vp, _vp, _vp, _vp, _vp, C.c_float, _vp, _vp, _vp, _vp])
 
@@ -108,16 +108,21 @@ def compact_rows(mask, tensors):
         t = t.detach()
         src.append(t if t.is_contiguous() else t.contiguous())
         out.append(torch.empty_like(src[-1]))
-    n = len(src)
+    # zero-width arrays (f_rest at sh_degree 0 is [n, 0, 3]) carry no bytes: only their row count changes
+    live = [k for k, t in enumerate(src) if rows and t.numel() // rows > 0]
+    if not live or rows == 0:
+        count = int(keep.sum().item())
+        return [o[:count] for o in out]
+    n = len(live)
     count = 0
     with torch.cuda.device(dev):
         for i in range(0, n, 40):
             m = min(40, n - i)
             S, D, RB = (_vp * m)(), (_vp * m)(), (C.c_int * m)()
             for k in range(m):
-                t = src[i + k]
-                S[k], D[k] = t.data_ptr(), out[i + k].data_ptr()
-                RB[k] = (t.numel() // max(rows, 1)) * t.element_size() if rows else t.element_size()
+                t = src[live[i + k]]
+                S[k], D[k] = t.data_ptr(), out[live[i + k]].data_ptr()
+                RB[k] = (t.numel() // rows) * t.element_size()
             count = int(check(lib.gsicp_table_compact(rows, keep.data_ptr(), m, S, D, RB, _stream(dev)), "gsicp_table_compact"))
     return [o[:count] for o in out]
 

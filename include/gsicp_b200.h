@@ -279,6 +279,7 @@ int gsicp_mapping_loss_backward(int H, int W, const float* d_image, const float*
  * gsicp_adam_step: torch.optim.Adam(..., eps=1e-15).step() for up to 8 parameter tensors in ONE launch
  *   (gaussian_model.py:214-225 builds six groups with their own lr; mp_Mapper.py:248 steps them).  Host arrays of device
  *   pointers; counts in elements; `step` is the 1-based step number after the increment, like Adam's state["step"].
+ *   The hyper-parameters are doubles: (1 - beta) is formed in double and rounded to float once, as PyTorch does.
  * gsicp_table_compact: boolean-mask row selection (prune_points / _prune_optimizer, gaussian_model.py:409-446) of n_arrays
  *   row-major arrays sharing one mask: dst[k][j] = src[k][i] for the j-th kept row i.  Returns the kept-row count (>= 0) or
  *   a negative error; dst buffers must hold `rows` rows.
@@ -286,8 +287,8 @@ int gsicp_mapping_loss_backward(int H, int W, const float* d_image, const float*
  *   trackable != 0, compacted as (xyz, normalised rotation xyzw, exp(scaling)) into device buffers of P rows; returns the
  *   count.  The outputs go to gsicp_gicp_set_input_target_device / set_target_covariances_fromqs_device without a D2H copy. */
 int gsicp_adam_step(int n_tensors, float* const* d_params, const float* const* d_grads, float* const* d_exp_avg,
-                    float* const* d_exp_avg_sq, const size_t* counts, const float* lrs, int step, float beta1, float beta2,
-                    float eps, void* stream);
+                    float* const* d_exp_avg_sq, const size_t* counts, const float* lrs, int step, double beta1, double beta2,
+                    double eps, void* stream);
 long long gsicp_table_compact(int rows, const uint8_t* d_keep, int n_arrays, const void* const* d_src, void* const* d_dst,
                               const int* row_bytes, void* stream);
 long long gsicp_trackable_target(int P, const float* d_xyz, const float* d_rotation_raw, const float* d_scaling_raw,

@@ -1,9 +1,17 @@
-"""The device-side exchange protocols of csrc/comm.cuh on ONE GPU: two "ranks" of an exchange group live in this process
+"""The device-side exchange protocols of csrc/comm.cuh on ONE GPU: two "ranks" of an exchange group live in one process
 (gsicp_comm_connect_local: plain device pointers instead of CUDA IPC handles), each driven by its own host thread and
 stream.  Point-sharded GICP — k-NN covariances, the persistent LM kernel (in-kernel exchange at every reduction point)
 and the host-driven kernels (exchange in the last block) — must reproduce the unsharded result; so must the sum-merged
-getters.  The real multi-process / NVLink path is tests/test_multigpu_gpu.py (needs >= 2 GPUs)."""
+getters.  The real multi-process / NVLink path is tests/test_multigpu_gpu.py (needs >= 2 GPUs).
+
+Two ranks sharing ONE CUDA context is an emulation with a hazard the real layout (one process and one context per GPU)
+does not have: anything that synchronises the whole context while a peer's kernel spins on a flag deadlocks — lazy module
+loading of a kernel's first launch does, and so does cudaFree/cudaHostAlloc.  So the ranks run in a child process with
+CUDA_MODULE_LOADING=EAGER, and every handle does one unsharded pass first (all scratch sized, nothing left to allocate)."""
 import ctypes as C
+import os
+import subprocess
+import sys
 import threading
 
 import numpy as np
@@ -43,7 +51,7 @@ def _run_ranks(world, fn):
     for t in th:
         t.start()
     for t in th:
-        t.join(timeout=300)
+        t.join(timeout=200)
     for e in err:
         if e is not None:
             raise e
@@ -51,8 +59,8 @@ def _run_ranks(world, fn):
     return out
 
 
-@pytest.mark.parametrize("host_lm", [False, True])
-def test_two_ranks_on_one_gpu_match_single(cuda, host_lm):
+def _two_ranks_match_single(host_lm):
+    import gs_icp_slam_b200  # noqa: F401  (registers the drop-in module names)
     import pygicp
     from gs_icp_slam_b200._lib import lib
 
@@ -61,11 +69,14 @@ def test_two_ranks_on_one_gpu_match_single(cuda, host_lm):
     trk = np.arange(0, len(src), 3)  # a trackable subset: covariance slots differ from point indices
     filt_s = S.trackable_filter(len(src), trk)
 
-    def align(comm, stream):
+    def make():
         r = pygicp.FastGICP()
         r.set_max_correspondence_distance(0.05)
         r.set_max_knn_distance(99999)
         r.set_host_lm(host_lm)
+        return r
+
+    def align(r, comm, stream):
         if stream is not None:
             r.set_stream(stream.cuda_stream)
         if comm is not None:
@@ -84,11 +95,17 @@ def test_two_ranks_on_one_gpu_match_single(cuda, host_lm):
             r.set_comm(None)
         return res
 
-    single = align(None, None)
+    cuda = torch.device("cuda", 0)
+    single = align(make(), None, None)
     comms = _group(2)
     try:
         streams = [torch.cuda.Stream(device=cuda) for _ in range(2)]
-        ranks = _run_ranks(2, lambda r: align(comms[r], streams[r]))
+        regs = [make() for _ in range(2)]
+        for r in range(2):  # unsharded pass on the rank's own stream: every buffer exists before a peer can spin
+            warm = align(regs[r], None, streams[r])
+            assert np.array_equal(warm[1][0], single[1][0])
+        torch.cuda.synchronize()
+        ranks = _run_ranks(2, lambda r: align(regs[r], comms[r], streams[r]))
     finally:
         torch.cuda.synchronize()
         for c in comms:
@@ -102,3 +119,19 @@ def test_two_ranks_on_one_gpu_match_single(cuda, host_lm):
             assert np.abs(a[5] - b[5]).max() <= 1e-9 * np.abs(b[5]).max()
     # both ranks hold bit-identical poses (the redundant LM decisions stayed in lock step)
     assert np.array_equal(ranks[0][0][0], ranks[1][0][0]) and np.array_equal(ranks[0][1][0], ranks[1][1][0])
+
+
+
+@pytest.mark.parametrize("host_lm", [False, True])
+def test_two_ranks_on_one_gpu_match_single(cuda, host_lm):
+    env = dict(os.environ, CUDA_MODULE_LOADING="EAGER")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env["PYTHONPATH"] = root + os.pathsep + env.get("PYTHONPATH", "")
+    p = subprocess.run([sys.executable, os.path.abspath(__file__), str(int(host_lm))], env=env, cwd=root, capture_output=True,
+                       text=True, timeout=280)
+    assert p.returncode == 0 and "EXCHANGE-OK" in p.stdout, p.stdout[-2000:] + p.stderr[-4000:]
+
+
+if __name__ == "__main__":
+    _two_ranks_match_single(bool(int(sys.argv[1])))
+    print("EXCHANGE-OK")

@@ -10,6 +10,12 @@ from unittest import mock
 
 import pytest
 
+try:  # native extension modules must not be dropped from sys.modules and re-imported (OpenCV breaks on a second import)
+    import cv2  # noqa: F401
+    import scipy.spatial.transform  # noqa: F401
+except Exception:
+    pass
+
 REF = "/root/reference"
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 pytestmark = pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present")
