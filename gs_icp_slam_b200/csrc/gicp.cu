@@ -556,8 +556,9 @@ struct LmResult {  // lives in mapped pinned host memory; written by block 0
   int converged;
   int status;             // 0 ok, 1 "lm not converged" (step_lm returned false), 3 grid barrier / peer exchange timed out
   int n_lin, n_err;
-  int pad;
+  int n_marks;            // phase timestamps recorded (GSICP_LM_MARKS=1; tools/prof_align.py)
   unsigned long long seq;
+  unsigned long long marks[48];  // %globaltimer of block 0 at: start, then after L, reduce, trial, E, reduce per phase
 };
 
 struct LmArgs {
@@ -581,6 +582,7 @@ struct LmArgs {
   Iso guess;
   LmResult* result;          // device alias of the mapped host block
   unsigned long long seq;
+  int marks;                 // record phase timestamps into result->marks (profiling aid)
 };
 
 __device__ __forceinline__ PoseD make_pose_dev(const Iso& x) {
@@ -694,6 +696,15 @@ align_lm_kernel(LmArgs a) {
   }
   __syncthreads();
 
+  int n_marks = 0;
+  auto mark = [&]() {
+    if (a.marks && blockIdx.x == 0 && threadIdx.x == 0 && n_marks < 48) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      a.result->marks[n_marks++] = t;
+    }
+  };
+  mark();
   unsigned int epoch = 0;  // thread 0's barrier target
   unsigned long long xseq = a.xseq;
   int iterations = 0, converged = 0, status = 0, n_lin = 0, n_err = 0;
@@ -731,10 +742,12 @@ align_lm_kernel(LmArgs a) {
       }
       block_sum_store<kRed>(v, a.partL + (size_t)blockIdx.x * kRed);
     }
+    mark();  // L done in block 0
     if (!grid_barrier(a.barrier, epoch)) {
       status = 3;
       break;
     }
+    mark();  // barrier passed
     if (a.comm.active()) {
       // this rank's sums go to every peer's segment (block 0), then every block of every rank adds the world's slots in
       // rank order: H, b, y0 are bit-identical on all ranks and the redundant LM decision stays in lock step
@@ -751,6 +764,7 @@ align_lm_kernel(LmArgs a) {
       reduce_partials<kRed>(a.partL, gridDim.x, s_sum);
     }
     n_lin++;
+    mark();  // H, b, y0 reduced
     if (threadIdx.x == 0) {
       int o = 0;
       for (int r = 0; r < 6; r++)
@@ -775,6 +789,7 @@ align_lm_kernel(LmArgs a) {
     for (; trial < a.lm_max_iterations; trial++) {
       if (threadIdx.x == 0) lm_trial(s_H, s_b, s_lambda, s_x0, s_d, s_delta, s_xi);
       __syncthreads();
+      mark();  // trial solved
       // phase E: error at xi with frozen correspondences
       {
         const PoseD T = make_pose_dev(s_xi);
@@ -785,10 +800,12 @@ align_lm_kernel(LmArgs a) {
         }
         block_sum_store<1>(v, a.partE + (size_t)(trial & 1) * gridDim.x + blockIdx.x);
       }
+      mark();  // E done in block 0
       if (!grid_barrier(a.barrier, epoch)) {
         status = 3;
         break;
       }
+      mark();  // barrier passed
       __shared__ double s_yi[1];
       if (a.comm.active()) {
         if (blockIdx.x == 0) {
@@ -804,6 +821,7 @@ align_lm_kernel(LmArgs a) {
         reduce_partials<1>(a.partE + (size_t)(trial & 1) * gridDim.x, gridDim.x, s_yi);
       }
       n_err++;
+      mark();  // error reduced
       if (threadIdx.x == 0) {
         const double yi = s_yi[0];
         double dot = 0.0;
@@ -848,6 +866,8 @@ align_lm_kernel(LmArgs a) {
     r->status = status;
     r->n_lin = n_lin;
     r->n_err = n_err;
+    mark();
+    r->n_marks = n_marks;
     __threadfence_system();
     *(volatile unsigned long long*)&r->seq = a.seq;
     __threadfence_system();
@@ -1556,6 +1576,8 @@ int run_align_device(gsicp_gicp* h, Iso& x0) {
   a.guess = x0;
   a.result = h->d_lm;
   a.seq = ++h->seq;
+  static const int s_marks = [] { const char* e = getenv("GSICP_LM_MARKS"); return e ? atoi(e) : 0; }();
+  a.marks = s_marks;
   {
     ProfScope ps(kProfLinearize, h->stream);  // slot "gicp_linearize": the whole device-resident LM loop
     GSICP_LAUNCH(align_lm_kernel, blocks, kLmBlock, 0, h->stream, a);
@@ -1581,6 +1603,11 @@ int run_align_device(gsicp_gicp* h, Iso& x0) {
     }
   }
   const LmResult r = *h->h_lm;
+  if (s_marks && r.n_marks > 1) {
+    fprintf(stderr, "[lm marks] total %.1f us:", (double)(r.marks[r.n_marks - 1] - r.marks[0]) * 1e-3);
+    for (int i = 1; i < r.n_marks; i++) fprintf(stderr, " %.1f", (double)(r.marks[i] - r.marks[i - 1]) * 1e-3);
+    fprintf(stderr, "\n");
+  }
   for (int i = 0; i < 3; i++) {
     for (int j = 0; j < 3; j++) x0.R[i][j] = r.R[3 * i + j];
     x0.t[i] = r.t[i];

@@ -52,6 +52,24 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], float a0, float a1, floa
       : "r"(__float_as_uint(a0)), "r"(__float_as_uint(a1)), "r"(__float_as_uint(a2)), "r"(__float_as_uint(a3)),
         "r"(__float_as_uint(b0)), "r"(__float_as_uint(b1)));
 }
+// Shared-memory accesses by 32-bit window address + immediate offset: with the addresses formed once per chunk / per thread
+// the survivor loop carries no address arithmetic (the compiler otherwise rebuilds the window base every iteration
+// under the 64-register cap).
+template <int kOff>
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4+%5];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr), "n"(kOff));
+  return v;
+}
+template <int kOff>
+__device__ __forceinline__ void sts32(uint32_t addr, float v) {
+  asm volatile("st.shared.f32 [%0+%1], %2;" ::"r"(addr), "n"(kOff), "f"(v) : "memory");
+}
+__device__ __forceinline__ float rcp_approx(float x) {  // MUFU.RCP, 1 ulp; the backward's tolerance is 2e-4 of the maximum
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
 // x = hi + lo with hi exactly representable in tf32 (lo keeps the next 11 bits once the MMA drops its own low bits)
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
 
@@ -142,12 +160,18 @@ render_backward_kernel(const uint32_t* __restrict__ tile_order, const uint2* __r
   float* const myW = sm.wq[warp];
   const int wpos = (lane & 3) * 8 + (lane >> 2);  // pixel k = lane sits at word (k & 3) * 8 + (k >> 2): the 8 pixels a
                                                   // thread needs for its B fragments are 8 consecutive words
+  constexpr int kOffB = 2 * kStage * 16, kOffC = 4 * kStage * 16;           // sm.b / sm.c relative to sm.a (same buffer)
+  constexpr int kOffW = kWarps * kGrp * kRow * 4;                           // sm.wq relative to sm.tq
+  const uint32_t s_base = (uint32_t)__cvta_generic_to_shared(smem_raw);
+  uint32_t s_slot = (uint32_t)__cvta_generic_to_shared(myT + wpos);         // this lane's word of survivor slot 0
+  asm volatile("" : "+r"(s_slot));                                          // opaque: one register, never rebuilt in the loop
   int cnt = 0;                                    // survivors staged in the current group (warp-uniform)
   float m_cx = 0.f, m_cy = 0.f;                   // lane s: centre of survivor s in the warp's frame, and its Gaussian
   uint32_t m_id = 0;
 
   // Reduce the staged group: D = A * B on the tensor cores, shift the pixel-frame moments to each Gaussian's centre,
   // one fp32 RED per moment.
+  const bool r_1 = g8 == 1, r_2 = g8 == 2, r_3 = g8 == 3, r_4 = g8 == 4, r_5 = g8 == 5;
   auto flush = [&]() {
     for (int s2 = cnt; s2 < kGrp; s2++) {  // unused slots contribute zero
       myT[s2 * kRow + wpos] = 0.f;
@@ -188,14 +212,15 @@ render_backward_kernel(const uint32_t* __restrict__ tile_order, const uint2* __r
       const float V0 = __shfl_sync(0xffffffffu, own_w, t4);
       const float cx = __shfl_sync(0xffffffffu, m_cx, n), cy = __shfl_sync(0xffffffffu, m_cy, n);
       const uint32_t gid = __shfl_sync(0xffffffffu, m_id, n);
-      // dx = cx - i, dy = cy - j: sum f dx = cx S0 - S_i, sum f dx^2 = cx^2 S0 - 2 cx S_i + S_ii, ...
-      float gt, gw = own_w;
-      if (g8 == 0)      { gt = own_t; }
-      else if (g8 == 1) { gt = cx * S0 - own_t;                            gw = cx * V0 - own_w; }
-      else if (g8 == 2) { gt = cy * S0 - own_t;                            gw = cy * V0 - own_w; }
-      else if (g8 == 3) { gt = own_t + cx * (cx * S0 - 2.f * S1); }
-      else if (g8 == 4) { gt = own_t + (cx * cy * S0 - cx * S2 - cy * S1); }
-      else              { gt = own_t + cy * (cy * S0 - 2.f * S2); }
+      // dx = cx - i, dy = cy - j: sum f dx = cx S0 - S_i, sum f dx^2 = cx^2 S0 - 2 cx S_i + S_ii, ... as one branch-free
+      // form  gt = +-own_t + p q S0 - (p Sb + q Sa)  with per-row selections of p, q in {0, 1, cx, cy}:
+      //   row 0: own_t | 1: cx S0 - own_t | 2: cy S0 - own_t | 3: own_t + cx^2 S0 - 2 cx S1
+      //   row 4: own_t + cx cy S0 - cx S2 - cy S1 | 5: own_t + cy^2 S0 - 2 cy S2
+      const float p = (r_1 | r_3 | r_4) ? cx : (r_2 | r_5) ? cy : 0.f;
+      const float q = r_3 ? cx : (r_4 | r_5) ? cy : 1.f;
+      const float cross = (g8 >= 3) ? p * (r_3 ? S1 : S2) + q * (r_5 ? S2 : S1) : 0.f;
+      const float gt = ((r_1 | r_2) ? -own_t : own_t) + (p * q) * S0 - cross;
+      const float gw = (r_1 | r_2) ? p * V0 - own_w : own_w;
       if (g8 < 6 && n < cnt) {
         float* dst = moments + (size_t)gid * kG;
         atomicAdd(dst + g8, gt);
@@ -230,16 +255,18 @@ render_backward_kernel(const uint32_t* __restrict__ tile_order, const uint2* __r
 
     const int first_pos = total - base;  // 1-based contributor id of slot 0
     if (first_pos - (n - 1) > warp_last) continue;  // the whole batch lies behind this warp's last contributor
-    const float4* sA = sm.a[buf];
-    const float4* sB = sm.b[buf];
-    const float4* sC = sm.c[buf];
     for (int c0 = 0; c0 < n; c0 += 32) {
       if (first_pos - c0 - 31 > warp_last && c0 + 32 <= n) continue;  // whole chunk behind the last contributor
+      uint32_t s_chunk = s_base + (uint32_t)(buf * kStage + c0) * 16u;  // sm.a[buf][c0]
+      asm volatile("" : "+r"(s_chunk));  // opaque: keep it in a register instead of rebuilding it per survivor
       uint32_t mask;
       {
         const int j = c0 + lane;
         bool hit = (j < n) && (first_pos - j <= warp_last);
-        if (kCull) hit = hit && subtile_hit(sA[j < n ? j : 0], sB[j < n ? j : 0], wx0f, wy0f, 7.f, 3.f);
+        if (kCull) {
+          const uint32_t s_j = s_chunk + (uint32_t)(j < n ? lane : 0) * 16u;
+          hit = hit && subtile_hit(lds128<0>(s_j), lds128<kOffB>(s_j), wx0f, wy0f, 7.f, 3.f);
+        }
         mask = __ballot_sync(0xffffffffu, hit);
       }
       while (mask) {
@@ -247,7 +274,8 @@ render_backward_kernel(const uint32_t* __restrict__ tile_order, const uint2* __r
         mask &= mask - 1;
         const int j = c0 + bit;
         const int contributor = first_pos - j;  // 1-based; reference compares (contributor-1) >= last (backward.cu:540-542)
-        const float4 a = sA[j], b = sB[j];
+        const uint32_t s_j = s_chunk + (uint32_t)bit * 16u;
+        const float4 a = lds128<0>(s_j), b = lds128<kOffB>(s_j);
         const float dx = a.x - pxf, dy = a.y - pyf;
         const float power = -0.5f * (a.z * dx * dx + b.x * dy * dy) - a.w * dx * dy;
         const float G = expf(power);
@@ -258,8 +286,8 @@ render_backward_kernel(const uint32_t* __restrict__ tile_order, const uint2* __r
 
         float tq = 0.f, wq = 0.f;
         if (active) {
-          const float4 c = sC[j];
-          const float inv = __frcp_rn(1.f - alpha);  // correctly rounded reciprocal, shared by the three divisions
+          const float4 c = lds128<kOffC>(s_j);
+          const float inv = rcp_approx(1.f - alpha);  // one reciprocal shared by the three divisions
           T = T * inv;                               // transmittance in front of this Gaussian (backward.cu:555)
           wq = alpha * T;                            // d(pixel channel)/d(colour), also d(pixel depth)/d(depth)
 
@@ -277,8 +305,11 @@ render_backward_kernel(const uint32_t* __restrict__ tile_order, const uint2* __r
                              bg_term * inv;
           tq = G * dsum;
         }
-        myT[cnt * kRow + wpos] = tq;
-        myW[cnt * kRow + wpos] = wq;
+        {
+          const uint32_t s_dst = s_slot + (uint32_t)cnt * (kRow * 4);
+          sts32<0>(s_dst, tq);
+          sts32<kOffW>(s_dst, wq);
+        }
         if (lane == cnt) {
           m_cx = a.x - wx0f;
           m_cy = a.y - wy0f;

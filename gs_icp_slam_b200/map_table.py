@@ -149,6 +149,69 @@ def _inverse_sigmoid(x):
 C0 = 0.28209479177387814
 
 
+# ---- N4: scene.ply (scene/gaussian_model.py:269-281, 619-636, 350-385) --------------------------------------------------
+def ply_attribute_names(n_dc, n_rest, n_scale=3, n_rot=4):
+    """construct_list_of_attributes (gaussian_model.py:269-281): x y z nx ny nz f_dc_* f_rest_* opacity scale_* rot_*."""
+    return (["x", "y", "z", "nx", "ny", "nz"] + [f"f_dc_{i}" for i in range(n_dc)] + [f"f_rest_{i}" for i in range(n_rest)] +
+            ["opacity"] + [f"scale_{i}" for i in range(n_scale)] + [f"rot_{i}" for i in range(n_rot)])
+
+
+def write_scene_ply(path, xyz, features_dc, features_rest, opacity, scaling, rotation):
+    """The reference's GaussianModel.save_ply (gaussian_model.py:619-636): one `vertex` element of float32 properties,
+    binary little endian.  The attribute table is assembled on the tensors' device ([N, C] in one concatenation, features
+    channel-major like the reference's transpose(1, 2).flatten) and leaves it in ONE copy; the reference builds N Python
+    tuples.  Same bytes as plyfile writes for that element."""
+    import os
+
+    import numpy as np
+
+    n = xyz.shape[0]
+    dc = features_dc.detach().transpose(1, 2).reshape(n, features_dc.shape[1] * features_dc.shape[2])
+    rest = features_rest.detach().transpose(1, 2).reshape(n, features_rest.shape[1] * features_rest.shape[2])
+    table = torch.cat((xyz.detach(), torch.zeros_like(xyz), dc, rest, opacity.detach().reshape(n, 1), scaling.detach(),
+                       rotation.detach()), dim=1).to(torch.float32).contiguous()
+    names = ply_attribute_names(dc.shape[1], rest.shape[1], scaling.shape[1], rotation.shape[1])
+    assert table.shape[1] == len(names)
+    head = ["ply", "format binary_little_endian 1.0", f"element vertex {n}"] + [f"property float {a}" for a in names] + ["end_header"]
+    d = os.path.dirname(path)
+    if d:
+        os.makedirs(d, exist_ok=True)
+    host = table.cpu().numpy().astype("<f4", copy=False)
+    with open(path, "wb") as f:
+        f.write(("\n".join(head) + "\n").encode("ascii"))
+        f.write(np.ascontiguousarray(host).tobytes())
+    return n
+
+
+def read_scene_ply(path, max_sh_degree):
+    """The reference's load_ply (gaussian_model.py:350-385): returns float32 tensors (CPU) in the model's layout:
+    xyz [N,3], features_dc [N,1,3], features_rest [N,(D+1)^2-1,3], opacity [N,1], scaling [N,3], rotation [N,4]."""
+    import numpy as np
+
+    with open(path, "rb") as f:
+        blob = f.read()
+    end = blob.index(b"end_header\n") + len(b"end_header\n")
+    lines = blob[:end].decode("ascii").split("\n")
+    if lines[0] != "ply" or not lines[1].startswith("format binary_little_endian"):
+        raise ValueError("not a binary little-endian ply file")
+    n = next(int(l.split()[2]) for l in lines if l.startswith("element vertex"))
+    props = [l.split() for l in lines if l.startswith("property ")]
+    if any(p[1] != "float" for p in props):
+        raise ValueError("scene.ply holds float properties only")
+    names = [p[2] for p in props]
+    tab = np.frombuffer(blob, dtype="<f4", count=n * len(names), offset=end).reshape(n, len(names))
+    col = {a: i for i, a in enumerate(names)}
+    pick = lambda prefix: sorted((a for a in names if a.startswith(prefix)), key=lambda a: int(a.split("_")[-1]))
+    t = lambda cols: torch.from_numpy(np.ascontiguousarray(tab[:, [col[c] for c in cols]]))
+    m = (max_sh_degree + 1) ** 2
+    rest = pick("f_rest_")
+    if len(rest) != 3 * (m - 1):
+        raise ValueError(f"f_rest has {len(rest)} columns, sh degree {max_sh_degree} needs {3 * (m - 1)}")
+    return {"xyz": t(["x", "y", "z"]), "f_dc": t(pick("f_dc_")).reshape(n, 3, 1).transpose(1, 2).contiguous(),
+            "f_rest": t(rest).reshape(n, 3, m - 1).transpose(1, 2).contiguous(), "opacity": t(["opacity"]),
+            "scaling": t(pick("scale_")), "rotation": t(pick("rot_"))}
+
+
 class GaussianTable:
     """The part of the reference's GaussianModel that the mapper loop drives (scene/gaussian_model.py), with the fused
     optimizer step, one-pass pruning and the on-device target hand-over."""
@@ -187,6 +250,19 @@ class GaussianTable:
     @property
     def get_features(self):
         return torch.cat((self._features_dc, self._features_rest), dim=1)
+
+    def save_ply(self, path):
+        """gaussian_model.py:619-636."""
+        return write_scene_ply(path, self._xyz, self._features_dc, self._features_rest, self._opacity, self._scaling, self._rotation)
+
+    def load_ply(self, path):
+        """gaussian_model.py:350-385: parameters from a scene.ply; the active SH degree becomes the maximum one."""
+        d = {k: v.to(self.device) for k, v in read_scene_ply(path, self.max_sh_degree).items()}
+        self._set(d)
+        self.active_sh_degree = self.max_sh_degree
+        n = self._xyz.shape[0]
+        self.trackable_mask = torch.zeros(n, dtype=torch.bool, device=self.device)
+        self.max_radii2D = torch.zeros(n, device=self.device)
 
     def params(self):
         return {"xyz": self._xyz, "f_dc": self._features_dc, "f_rest": self._features_rest, "opacity": self._opacity,
