@@ -61,8 +61,9 @@ def parse():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="c3", choices=["c3", "c2", "c4", "c5"],
+    ap.add_argument("--config", default="c3", choices=["c3", "c2", "c1", "c4", "c5"],
                     help="c3 (default, the metric's config): TUM-shape 640x480, 300k Gaussians; c2: Replica-shape, 100k Gaussians; "
+                         "c1: GICP align of two 10k-point clouds (the reference's CPU-runnable case); "
                          "c4 / c5: the large rasterizer-only / GICP-only strong-scaling configs")
     ap.add_argument("--gaussians", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -80,7 +81,7 @@ def parse():
     if a.warmup < 3:
         a.warmup = 3
     if a.gaussians is None:
-        a.gaussians = {"c3": 300000, "c2": 100000, "c4": 1000000, "c5": 2000000}[a.config]
+        a.gaussians = {"c3": 300000, "c2": 100000, "c1": 10000, "c4": 1000000, "c5": 2000000}[a.config]
     return a
 
 
@@ -674,7 +675,7 @@ def main():
     rank = int(os.environ.get("RANK", 0))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
-    if args.config in ("c4", "c5"):
+    if args.config in ("c1", "c4", "c5"):
         from tools import bench_large
 
         return bench_large.main(args, rank, local_rank, world)

@@ -122,16 +122,17 @@ def _two_ranks_match_single(host_lm):
 
 
 
-@pytest.mark.parametrize("host_lm", [False, True])
-def test_two_ranks_on_one_gpu_match_single(cuda, host_lm):
+def test_two_ranks_on_one_gpu_match_single(cuda):
+    """Both LM drivers (persistent kernel with in-kernel exchange; host-driven kernels with the exchange in the last block) in
+    ONE child process: eager module loading costs about a minute of start-up."""
     env = dict(os.environ, CUDA_MODULE_LOADING="EAGER")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     env["PYTHONPATH"] = root + os.pathsep + env.get("PYTHONPATH", "")
-    p = subprocess.run([sys.executable, os.path.abspath(__file__), str(int(host_lm))], env=env, cwd=root, capture_output=True,
-                       text=True, timeout=280)
-    assert p.returncode == 0 and "EXCHANGE-OK" in p.stdout, p.stdout[-2000:] + p.stderr[-4000:]
+    p = subprocess.run([sys.executable, os.path.abspath(__file__)], env=env, cwd=root, capture_output=True, text=True, timeout=280)
+    assert p.returncode == 0 and "EXCHANGE-OK False" in p.stdout and "EXCHANGE-OK True" in p.stdout, p.stdout[-2000:] + p.stderr[-4000:]
 
 
 if __name__ == "__main__":
-    _two_ranks_match_single(bool(int(sys.argv[1])))
-    print("EXCHANGE-OK")
+    for host_lm in (False, True):
+        _two_ranks_match_single(host_lm)
+        print("EXCHANGE-OK", host_lm, flush=True)

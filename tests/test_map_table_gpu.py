@@ -147,7 +147,9 @@ def test_table_matches_reference_bookkeeping_and_hands_over_on_device(cuda):
     with torch.no_grad():
         sel = torch.logical_and((tab.get_opacity > th).squeeze(-1), tab.trackable_mask)
         assert tp.is_cuda and torch.equal(tp, tab.get_xyz[sel])
-        assert torch.allclose(tr, tab.get_rotation[sel], rtol=0, atol=1e-7) and torch.allclose(ts, tab.get_scaling[sel], rtol=1e-6)
+        # normalize / exp evaluated in one kernel instead of torch's reduction + division kernels: 2 ulp of a unit quaternion
+        assert torch.allclose(tr, tab.get_rotation[sel], rtol=0, atol=2.5e-7), float((tr - tab.get_rotation[sel]).abs().max())
+        assert torch.allclose(ts, tab.get_scaling[sel], rtol=2e-6, atol=0), float((ts / tab.get_scaling[sel] - 1).abs().max())
     # hand-over: same registration result as feeding the tracker the reference's CPU copies
     cam = S.TUM
     pose = S.trajectory_pose(3, 200)

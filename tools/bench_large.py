@@ -1,4 +1,6 @@
-"""Large strong-scaling configs of bench.py (`--config c4|c5`), one process per GPU under torchrun:
+"""GICP-only / rasterizer-only configs of bench.py (`--config c1|c4|c5`), one process per GPU under torchrun:
+  C1: GICP align of two 10k-point clouds (the reference's own CPU-runnable case); `--impl reference` times the real
+      fast_gicp (oracle/_ref, all host threads) on the same pair
   C4: 1280x960, 1M Gaussians, rasterizer fwd+bwd only, tiles sharded over the ranks (moments exchange inside backward)
   C5: GICP align on a 2M x 2M point pair, source points sharded (28-double normal equations exchanged per linearize)
 Total work is fixed as N grows ("scaling": "strong").  A step = one raster fwd+bwd iteration (C4) / one align() (C5).
@@ -31,12 +33,59 @@ def _timed(fn, steps, warmup, world, dev, torch, dist, flush):
     return float(t.item()), ts
 
 
+_C1_WORKLOAD = ("C1: GICP align of a {n} x {n} point pair (seeds 0/1), identity guess, k-NN source covariances + LM loop, "
+                "max_corr 0.05; target covariances precomputed outside the step")
+
+
+def _c1_reference(args):
+    """The reference's tracker on C1: fast_gicp itself (oracle/_ref/fast_gicp, unmodified sources, OpenMP on every host
+    thread), same pair, same calls per step (set_input_source + set_source_filter + align with lazy source covariances)."""
+    from gs_icp_slam_b200 import synthetic as S
+    from oracle import ref_gicp
+
+    if not ref_gicp.available():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/fast_gicp not built (make -C oracle ref needs /root/reference)"}))
+        return
+    n = args.gaussians
+    tgt, src, T = S.gicp_pair(n, n)
+    reg = ref_gicp.FastGICP()
+    cores = os.cpu_count() or 1
+    reg.set_num_threads(cores)
+    reg.set_max_correspondence_distance(0.05)
+    reg.set_max_knn_distance(99999)
+    filt = np.arange(1, n + 1, dtype=np.int32)
+    reg.set_input_target(tgt)
+    reg.set_target_filter(n, filt)
+    reg.calculate_target_covariance_with_filter()
+    ts, pose = [], None
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        reg.set_input_source(src)
+        reg.set_source_filter(n, filt)  # the SLAM's fast_gicp indexes its covariance table through the filter: always set
+        pose = np.array(reg.align(np.eye(4, dtype=np.float32)))
+        if i >= args.warmup:
+            ts.append(time.perf_counter() - t0)
+    v = len(ts) / float(np.sum(ts))
+    print(json.dumps({"impl": "reference", "metric": "GICP align/sec (10k x 10k points)", "value": v, "unit": "aligns/s", "n_gpus": 1,
+                      "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / v, "higher_is_better": True, "scaling": "strong",
+                      "vs_baseline": None, "dtype": "f64 (GICP algebra on f32 points)", "data": "synthetic",
+                      "config": {"workload": _C1_WORKLOAD.format(n=n)},
+                      "cpu_baseline": {"value": v, "unit": "aligns/s", "cores": cores, "kind": "reference",
+                                       "sample": f"{args.steps} full aligns of the same pair"},
+                      "e2e": {"value": v, "unit": "aligns/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                      "pose_error_vs_ground_truth": float(np.abs(pose.astype(np.float64) - T).max())}))
+
+
 def main(args, rank, local_rank, world):
     import torch
 
     from gs_icp_slam_b200 import _lib, sharding
     from gs_icp_slam_b200 import synthetic as S
 
+    if args.impl == "reference" and args.config == "c1":
+        if rank == 0:
+            _c1_reference(args)
+        return
     if args.impl == "reference":
         if rank == 0:
             print(json.dumps({"impl": "reference", "unavailable": "the large configs have no reference arm: the reference's "
@@ -95,30 +144,41 @@ def main(args, rank, local_rank, world):
         import pygicp
 
         n = args.gaussians
-        tgt, src, T = S.gicp_pair(n, n, 6, 7, 0.001, scale=5.0)
+        c1 = args.config == "c1"
+        tgt, src, T = S.gicp_pair(n, n) if c1 else S.gicp_pair(n, n, 6, 7, 0.001, scale=5.0)
         reg = pygicp.FastGICP()
-        reg.set_max_correspondence_distance(0.25)
+        reg.set_max_correspondence_distance(0.05 if c1 else 0.25)
         reg.set_max_knn_distance(99999)
         if group is not None:
             group.attach_gicp(reg)
         reg.set_input_target(tgt)
-        reg.calculate_target_covariance()
+        if c1:
+            filt = np.arange(1, n + 1, dtype=np.int32)
+            reg.set_target_filter(n, filt)
+            reg.calculate_target_covariance_with_filter()
+        else:
+            reg.calculate_target_covariance()
         src_dev = torch.from_numpy(src.astype(np.float32)).to(dev)
         res = {}
 
         def it():
             reg.set_input_source(src_dev)   # new frame: source covariances are recomputed inside align (fgi:229-232)
+            if c1:
+                reg.set_source_filter(n, filt)
             res["pose"] = reg.align(np.eye(4, dtype=np.float32))
 
-        metric, unit = "GICP align/sec (2M x 2M points)", "aligns/s"
-        workload = f"C5: GICP align of a {n} x {n} point pair (seeds 6/7), k-NN source covariances + LM loop, max_corr 0.25"
+        metric, unit = ("GICP align/sec (10k x 10k points)" if c1 else "GICP align/sec (2M x 2M points)"), "aligns/s"
+        workload = (_C1_WORKLOAD.format(n=n) if c1 else
+                    f"C5: GICP align of a {n} x {n} point pair (seeds 6/7), k-NN source covariances + LM loop, max_corr 0.25")
         step = it
         extra["lm_iterations"] = lambda: reg.last_iterations
         extra["pose_error_vs_ground_truth"] = lambda: float(np.abs(res["pose"].astype(np.float64) - T).max())
 
     for _ in range(2):  # allocator / scratch growth, untimed
         step()
+    l0 = _lib.launch_count() if hasattr(_lib, "launch_count") else 0
     t_ms, ts = _timed(step, K, Wm, world, dev, torch, dist, flush)
+    launches = ((_lib.launch_count() - l0) * K) // (K + Wm) if hasattr(_lib, "launch_count") else 0
     _lib.prof_reset()
     _lib.prof_enable(True)
     for _ in range(min(K, 5)):
@@ -130,6 +190,7 @@ def main(args, rank, local_rank, world):
         out = {"metric": metric, "value": K / (t_ms * 1e-3), "unit": unit, "n_gpus": world, "steps": K, "warmup": Wm,
                "ms_per_step": t_ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                "dtype": "f32 (rasterizer)" if args.config == "c4" else "f64 (GICP algebra on f32 points)", "data": "synthetic",
+               "gpu_launches": int(launches),
                "config": {"workload": workload, "l2": "256 MiB write between steps, excluded from the per-step CUDA-event time"},
                "parallelism": "single GPU" if world == 1 else (f"{world} GPUs: " + ("screen tiles" if args.config == "c4" else "source points") +
                                                                 " sharded, " + (group.describe() if group else "")),
