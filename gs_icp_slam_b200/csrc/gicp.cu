@@ -653,6 +653,29 @@ __device__ __forceinline__ void block_sum_store(const double* v, double* __restr
   __syncthreads();
 }
 
+// Same result layout as block_sum_store, for values that are produced in several passes: each pass adds its warp sums into
+// the warp's row of s_acc (lane 0), block_acc_store then adds the rows in warp order.
+template <int NV>
+__device__ __forceinline__ void warp_acc_add(const double* v, double (*s_acc)[NV]) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < NV; k++) {
+    const double r = warp_sum_d(v[k]);
+    if (lane == 0) s_acc[warp][k] += r;
+  }
+}
+template <int NV>
+__device__ __forceinline__ void block_acc_store(double (*s_acc)[NV], double* __restrict__ out) {
+  __syncthreads();
+  if (threadIdx.x < NV) {
+    double r = 0.0;
+#pragma unroll
+    for (int w = 0; w < kLmBlock / 32; w++) r += s_acc[w][threadIdx.x];
+    out[threadIdx.x] = r;
+  }
+  __syncthreads();
+}
+
 // Sum partial[b][NV] over the blocks in a fixed order, identically in every block: thread (seg, k) adds the blocks
 // b = seg, seg + kLmSeg, ...; thread k < NV then adds the kLmSeg segment sums in order.  Result in s_out[NV].
 template <int NV>
@@ -678,6 +701,7 @@ __device__ __forceinline__ void reduce_partials(const double* __restrict__ parti
 __global__ void __launch_bounds__(kLmBlock, 2)
 align_lm_kernel(LmArgs a) {
   __shared__ double s_sum[kRed];
+  __shared__ double s_accL[kLmBlock / 32][kRed];
   __shared__ Iso s_x0, s_xi, s_delta;
   __shared__ double s_H[6][6], s_b[6], s_d[6];
   __shared__ double s_y0, s_lambda, s_nu;
@@ -713,34 +737,51 @@ align_lm_kernel(LmArgs a) {
     // ---------------- phase L: correspondences + linearisation at x0 ----------------
     {
       const PoseD T = make_pose_dev(s_x0);
-      double v[kRed];
-#pragma unroll
-      for (int k = 0; k < kRed; k++) v[k] = 0.0;
-      for (int c = gwarp; c < nchunks; c += total_warps) {
+      for (int k = lane; k < kRed; k += 32) s_accL[warp][k] = 0.0;
+      __syncwarp();
+      // A warp takes its chunks of kLmChunk points in groups of 32 / kLmChunk: the nearest-neighbour searches of one chunk
+      // run in lock step (grid_nn_warp_multi), lane 4 s + k keeps the match of point k of the group's s-th chunk, and ONE
+      // linearisation pass then serves the whole group with up to 32 lanes busy.
+      constexpr int kGroup = 32 / kLmChunk;
+      for (int cg = gwarp; cg < nchunks; cg += kGroup * total_warps) {
         int my_i = -1, my_j = -1;
+        for (int sl = 0; sl < kGroup; sl++) {
+          const int c = cg + sl * total_warps;
+          if (c >= nchunks) break;  // warp-uniform
+          const int i0 = a.begin + c * kLmChunk;
+          float tx[kLmChunk], ty[kLmChunk], tz[kLmChunk], d2[kLmChunk];
+          uint32_t id[kLmChunk];
 #pragma unroll
-        for (int k = 0; k < kLmChunk; k++) {
-          const int i = a.begin + c * kLmChunk + k;
-          if (i < a.end) {  // warp-uniform
+          for (int k = 0; k < kLmChunk; k++) {
+            const int i = min(i0 + k, a.end - 1);  // the tail of the last chunk repeats its last point (result unused)
             const float px = a.src_xyz[3 * (size_t)i], py = a.src_xyz[3 * (size_t)i + 1], pz = a.src_xyz[3 * (size_t)i + 2];
-            float tx, ty, tz, d2;
-            uint32_t id;
-            transform_f32(T, px, py, pz, tx, ty, tz);
-            grid_nn_warp(a.tgt, tx, ty, tz, d2, id);
-            const int32_t j = ((a.tgt.n > 0) && ((double)d2 < a.max_corr_sq)) ? (int32_t)id : -1;
-            if (lane == 0) {
-              a.sqd[i] = d2;
-              a.corr[i] = j;
-            }
-            if (lane == k) {
-              my_i = i;
-              my_j = j;
+            transform_f32(T, px, py, pz, tx[k], ty[k], tz[k]);
+          }
+          grid_nn_warp_multi<kLmChunk>(a.tgt, tx, ty, tz, d2, id);
+#pragma unroll
+          for (int k = 0; k < kLmChunk; k++) {
+            const int i = i0 + k;
+            if (i < a.end) {  // warp-uniform
+              const int32_t j = ((a.tgt.n > 0) && ((double)d2[k] < a.max_corr_sq)) ? (int32_t)id[k] : -1;
+              if (lane == 0) {
+                a.sqd[i] = d2[k];
+                a.corr[i] = j;
+              }
+              if (lane == sl * kLmChunk + k) {
+                my_i = i;
+                my_j = j;
+              }
             }
           }
         }
+        // the 28 sums live in registers only for the duration of this pass (the search above needs the registers)
+        double v[kRed];
+#pragma unroll
+        for (int k = 0; k < kRed; k++) v[k] = 0.0;
         if (my_j >= 0) linearize_point(T, my_i, my_j, a.src_xyz, a.src_cov, a.tgt_xyz, a.tgt_cov, a.mahal, v);
+        warp_acc_add<kRed>(v, s_accL);
       }
-      block_sum_store<kRed>(v, a.partL + (size_t)blockIdx.x * kRed);
+      block_acc_store<kRed>(s_accL, a.partL + (size_t)blockIdx.x * kRed);
     }
     mark();  // L done in block 0
     if (!grid_barrier(a.barrier, epoch)) {

@@ -663,4 +663,90 @@ __device__ __forceinline__ void grid_nn_warp(const GridView& g, float qx, float 
   }
 }
 
+// Nearest neighbour of Q query points at once (same result as Q calls of grid_nn_warp): the rings of the Q queries are
+// walked in lock step, so the cell-range loads and the candidate loads of all of them are in flight together — the search
+// of one point is a chain of dependent L2 round trips with little work in between, and a warp that walks them one point at
+// a time (align_lm_kernel runs 8 warps per SM) is latency bound.  A query that has met its exact stopping criterion is
+// skipped from then on.
+template <int Q>
+__device__ __forceinline__ void grid_nn_warp_multi(const GridView& g, const float (&qx)[Q], const float (&qy)[Q], const float (&qz)[Q],
+                                                   float (&out_d2)[Q], uint32_t (&out_id)[Q]) {
+  const int lane = threadIdx.x & 31;
+  float bd[Q];
+  uint32_t bi[Q];
+#pragma unroll
+  for (int q = 0; q < Q; q++) {
+    bd[q] = FLT_MAX;
+    bi[q] = 0xffffffffu;
+    out_d2[q] = FLT_MAX;
+    out_id[q] = 0xffffffffu;
+  }
+  if (g.n <= 0) return;
+  const GridMeta m = *g.meta;
+  int3 c0[Q];
+#pragma unroll
+  for (int q = 0; q < Q; q++) c0[q] = grid_cell_of(m, qx[q], qy[q], qz[q]);
+  unsigned done = 0;  // warp-uniform bit per query
+  constexpr unsigned kAll = (1u << Q) - 1u;
+  for (int r = 0; r <= kMaxRing && done != kAll; r++) {
+    const int nslots = 2 * (2 * r + 1) * (2 * r + 1);
+    for (int s0 = 0; s0 < nslots; s0 += 32) {
+      RingCursor c[Q];
+      uint32_t tmax = 0;
+#pragma unroll
+      for (int q = 0; q < Q; q++) {
+        c[q] = ring_slots(g, m, c0[q], r, s0, lane);
+        if ((done >> q) & 1u) c[q].total = 0;
+        tmax = max(tmax, c[q].total);
+      }
+      for (uint32_t t0 = 0; t0 < tmax; t0 += 32) {
+        const uint32_t t = t0 + lane;
+        float4 p[Q];
+        bool valid[Q];
+#pragma unroll
+        for (int q = 0; q < Q; q++) {
+          valid[q] = t < c[q].total;
+          const uint32_t idx = ring_element(c[q], valid[q] ? t : 0);
+          p[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (valid[q]) p[q] = g.pts[idx];
+        }
+#pragma unroll
+        for (int q = 0; q < Q; q++) {
+          if (valid[q]) {
+            const float d = dist2_nofma(p[q].x, p[q].y, p[q].z, qx[q], qy[q], qz[q]);
+            const uint32_t id = __float_as_uint(p[q].w);
+            if (d < bd[q] || (d == bd[q] && id < bi[q])) {
+              bd[q] = d;
+              bi[q] = id;
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < Q; q++) {
+      if ((done >> q) & 1u) continue;
+      bool all;
+      const float lim = ring_bound(m, c0[q], r, qx[q], qy[q], qz[q], all);
+      float d = bd[q];
+      uint32_t i = bi[q];
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) {
+        const float od = __shfl_xor_sync(0xffffffffu, d, o);
+        const uint32_t oi = __shfl_xor_sync(0xffffffffu, i, o);
+        if (od < d || (od == d && oi < i)) {
+          d = od;
+          i = oi;
+        }
+      }
+      out_d2[q] = d;
+      out_id[q] = i;
+      if (all || (lim > 0.f && d < lim)) done |= 1u << q;
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < Q; q++)  // far outside the occupied cells: the single-query search ends in its exact linear scan
+    if (!((done >> q) & 1u)) grid_nn_warp(g, qx[q], qy[q], qz[q], out_d2[q], out_id[q]);
+}
+
 }  // namespace gsicp
