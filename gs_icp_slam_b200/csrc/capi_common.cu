@@ -80,7 +80,7 @@ void prof_end(int k, cudaStream_t s) {
 static const char* kProfNames[gsicp::kProfCount] = {"preprocess", "tile_scan", "emit_instances", "tile_sort",
                                                     "render_forward", "render_backward", "gaussian_backward",
                                                     "gicp_covariance", "gicp_linearize", "gicp_error", "grid_build",
-                                                    "dist2", "loss_forward", "loss_backward"};
+                                                    "dist2", "loss_forward", "loss_backward", "moment_exchange"};
 
 extern "C" void gsicp_prof_enable(int on) { gsicp::g_prof_on = on != 0; }
 extern "C" void gsicp_prof_reset(void) {

@@ -27,6 +27,12 @@ __global__ void comm_barrier_kernel(CommView c, unsigned long long seq, int* sta
   }
 }
 
+int comm_preload_kernels() {
+  cudaFuncAttributes fa;
+  GSICP_CUDA(cudaFuncGetAttributes(&fa, (const void*)comm_barrier_kernel));
+  return GSICP_OK;
+}
+
 int comm_stream_barrier(gsicp_comm* c, cudaStream_t stream) {
   if (!c || !c->connected || c->world <= 1) return GSICP_OK;
   const unsigned long long seq = ++c->bar_seq;

@@ -720,6 +720,8 @@ align_lm_kernel(LmArgs a) {
   }
   __syncthreads();
 
+  GridMeta grid_meta = {};  // loaded once: the search would otherwise start every chunk with this dependent load
+  if (a.tgt.n > 0) grid_meta = *a.tgt.meta;
   int n_marks = 0;
   auto mark = [&]() {
     if (a.marks && blockIdx.x == 0 && threadIdx.x == 0 && n_marks < 48) {
@@ -757,7 +759,7 @@ align_lm_kernel(LmArgs a) {
             const float px = a.src_xyz[3 * (size_t)i], py = a.src_xyz[3 * (size_t)i + 1], pz = a.src_xyz[3 * (size_t)i + 2];
             transform_f32(T, px, py, pz, tx[k], ty[k], tz[k]);
           }
-          grid_nn_warp_multi<kLmChunk>(a.tgt, tx, ty, tz, d2, id);
+          grid_nn_warp_multi<kLmChunk>(a.tgt, grid_meta, tx, ty, tz, d2, id);
 #pragma unroll
           for (int k = 0; k < kLmChunk; k++) {
             const int i = i0 + k;
@@ -2019,3 +2021,23 @@ int gsicp_gicp_last_timing(gsicp_gicp* h, double out[5]) {
 }
 
 }  // extern "C"
+
+// Test hook (tests/test_exchange_gpu.py): load every kernel of this translation unit and of comm.cu now.  With CUDA's
+// default lazy module loading the FIRST launch of a kernel may synchronise the context; two exchange ranks emulated inside
+// one process / one context would then deadlock on a peer that spins on a flag.  One process per GPU (the real layout) never
+// needs this.
+namespace gsicp { int comm_preload_kernels(); }
+extern "C" int gsicp_test_preload_kernels(void) {
+  cudaFuncAttributes fa;
+  const void* fns[] = {(const void*)knn_kernel<10>, (const void*)knn_kernel<20>, (const void*)knn_kernel<32>,
+                       (const void*)covariance_kernel<10>, (const void*)covariance_kernel<20>, (const void*)covariance_kernel<32>,
+                       (const void*)compact_xyz_kernel, (const void*)cov_from_qs_kernel, (const void*)correspond_kernel,
+                       (const void*)fitness_kernel, (const void*)corr_pack_kernel, (const void*)corr_unpack_kernel,
+                       (const void*)linearize_kernel, (const void*)error_kernel, (const void*)align_lm_kernel,
+                       (const void*)f64_to_f32_kernel, (const void*)identity_filter_kernel,
+                       (const void*)comm_stage_kernel<int32_t>, (const void*)comm_stage_kernel<float>, (const void*)comm_stage_kernel<double>,
+                       (const void*)comm_stage_corr_kernel,
+                       (const void*)comm_sum_kernel<int32_t>, (const void*)comm_sum_kernel<float>, (const void*)comm_sum_kernel<double>};
+  for (const void* f : fns) GSICP_CUDA(cudaFuncGetAttributes(&fa, f));
+  return gsicp::comm_preload_kernels();
+}

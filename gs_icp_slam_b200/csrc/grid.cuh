@@ -663,14 +663,40 @@ __device__ __forceinline__ void grid_nn_warp(const GridView& g, float qx, float 
   }
 }
 
-// Nearest neighbour of Q query points at once (same result as Q calls of grid_nn_warp): the rings of the Q queries are
+// Slots of the whole 3x3x3 block around c0 (rings 0 and 1 together): cells are contiguous along x, so the block is 9
+// contiguous candidate ranges, one per (z, y) row — one round of cell_start loads instead of one per ring.
+__device__ __forceinline__ RingCursor block3_slots(const GridView& g, const GridMeta& m, int3 c0, int lane) {
+  uint32_t b = 0, e = 0;
+  if (lane < 9) {
+    const int z = c0.z + lane / 3 - 1, y = c0.y + lane % 3 - 1;
+    if (z >= 0 && z < m.nz && y >= 0 && y < m.ny) {
+      const int base = (z * m.ny + y) * m.nx;
+      b = g.cell_start[base + max(c0.x - 1, 0)];
+      e = g.cell_start[base + min(c0.x + 1, m.nx - 1) + 1];
+    }
+  }
+  const uint32_t len = e - b;
+  uint32_t incl = len;
+#pragma unroll
+  for (int o = 1; o < 16; o <<= 1) {  // only lanes 0..8 hold a slot
+    const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  RingCursor c;
+  c.b = b;
+  c.excl = incl - len;
+  c.total = __shfl_sync(0xffffffffu, incl, 31);
+  return c;
+}
+
+// Nearest neighbour of Q query points at once (same result as Q calls of grid_nn_warp): the searches of the Q queries are
 // walked in lock step, so the cell-range loads and the candidate loads of all of them are in flight together — the search
 // of one point is a chain of dependent L2 round trips with little work in between, and a warp that walks them one point at
-// a time (align_lm_kernel runs 8 warps per SM) is latency bound.  A query that has met its exact stopping criterion is
-// skipped from then on.
+// a time (align_lm_kernel runs 8 warps per SM) is latency bound.  The first pass takes rings 0 and 1 as one block
+// (block3_slots) and applies ring 1's exact stopping criterion; a query that has met it is skipped from then on.
 template <int Q>
-__device__ __forceinline__ void grid_nn_warp_multi(const GridView& g, const float (&qx)[Q], const float (&qy)[Q], const float (&qz)[Q],
-                                                   float (&out_d2)[Q], uint32_t (&out_id)[Q]) {
+__device__ __forceinline__ void grid_nn_warp_multi(const GridView& g, const GridMeta& m, const float (&qx)[Q], const float (&qy)[Q],
+                                                   const float (&qz)[Q], float (&out_d2)[Q], uint32_t (&out_id)[Q]) {
   const int lane = threadIdx.x & 31;
   float bd[Q];
   uint32_t bi[Q];
@@ -682,47 +708,41 @@ __device__ __forceinline__ void grid_nn_warp_multi(const GridView& g, const floa
     out_id[q] = 0xffffffffu;
   }
   if (g.n <= 0) return;
-  const GridMeta m = *g.meta;
   int3 c0[Q];
 #pragma unroll
   for (int q = 0; q < Q; q++) c0[q] = grid_cell_of(m, qx[q], qy[q], qz[q]);
   unsigned done = 0;  // warp-uniform bit per query
   constexpr unsigned kAll = (1u << Q) - 1u;
-  for (int r = 0; r <= kMaxRing && done != kAll; r++) {
-    const int nslots = 2 * (2 * r + 1) * (2 * r + 1);
-    for (int s0 = 0; s0 < nslots; s0 += 32) {
-      RingCursor c[Q];
-      uint32_t tmax = 0;
+
+  auto scan = [&](RingCursor (&c)[Q]) {  // read the flattened candidate lists of all queries, 32 per query and round
+    uint32_t tmax = 0;
+#pragma unroll
+    for (int q = 0; q < Q; q++) tmax = max(tmax, c[q].total);
+    for (uint32_t t0 = 0; t0 < tmax; t0 += 32) {
+      const uint32_t t = t0 + lane;
+      float4 p[Q];
+      bool valid[Q];
 #pragma unroll
       for (int q = 0; q < Q; q++) {
-        c[q] = ring_slots(g, m, c0[q], r, s0, lane);
-        if ((done >> q) & 1u) c[q].total = 0;
-        tmax = max(tmax, c[q].total);
+        valid[q] = t < c[q].total;
+        const uint32_t idx = ring_element(c[q], valid[q] ? t : 0);
+        p[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (valid[q]) p[q] = g.pts[idx];
       }
-      for (uint32_t t0 = 0; t0 < tmax; t0 += 32) {
-        const uint32_t t = t0 + lane;
-        float4 p[Q];
-        bool valid[Q];
 #pragma unroll
-        for (int q = 0; q < Q; q++) {
-          valid[q] = t < c[q].total;
-          const uint32_t idx = ring_element(c[q], valid[q] ? t : 0);
-          p[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (valid[q]) p[q] = g.pts[idx];
-        }
-#pragma unroll
-        for (int q = 0; q < Q; q++) {
-          if (valid[q]) {
-            const float d = dist2_nofma(p[q].x, p[q].y, p[q].z, qx[q], qy[q], qz[q]);
-            const uint32_t id = __float_as_uint(p[q].w);
-            if (d < bd[q] || (d == bd[q] && id < bi[q])) {
-              bd[q] = d;
-              bi[q] = id;
-            }
+      for (int q = 0; q < Q; q++) {
+        if (valid[q]) {
+          const float d = dist2_nofma(p[q].x, p[q].y, p[q].z, qx[q], qy[q], qz[q]);
+          const uint32_t id = __float_as_uint(p[q].w);
+          if (d < bd[q] || (d == bd[q] && id < bi[q])) {
+            bd[q] = d;
+            bi[q] = id;
           }
         }
       }
     }
+  };
+  auto settle = [&](int r) {  // warp argmin per query + the exact stopping criterion of ring r
 #pragma unroll
     for (int q = 0; q < Q; q++) {
       if ((done >> q) & 1u) continue;
@@ -743,6 +763,27 @@ __device__ __forceinline__ void grid_nn_warp_multi(const GridView& g, const floa
       out_id[q] = i;
       if (all || (lim > 0.f && d < lim)) done |= 1u << q;
     }
+  };
+
+  {
+    RingCursor c[Q];
+#pragma unroll
+    for (int q = 0; q < Q; q++) c[q] = block3_slots(g, m, c0[q], lane);
+    scan(c);
+    settle(1);
+  }
+  for (int r = 2; r <= kMaxRing && done != kAll; r++) {
+    const int nslots = 2 * (2 * r + 1) * (2 * r + 1);
+    for (int s0 = 0; s0 < nslots; s0 += 32) {
+      RingCursor c[Q];
+#pragma unroll
+      for (int q = 0; q < Q; q++) {
+        c[q] = ring_slots(g, m, c0[q], r, s0, lane);
+        if ((done >> q) & 1u) c[q].total = 0;
+      }
+      scan(c);
+    }
+    settle(r);
   }
 #pragma unroll
   for (int q = 0; q < Q; q++)  // far outside the occupied cells: the single-query search ends in its exact linear scan

@@ -36,7 +36,7 @@ void debug_sync_report(const char* kernel, cudaStream_t stream);
 // CUDA events recorded on the launching stream; totals are resolved when read.  Off by default.
 enum ProfKernel {
   kProfPreprocess = 0, kProfDepthSort, kProfEmit, kProfTileSort, kProfRenderFwd, kProfRenderBwd, kProfGaussBwd,
-  kProfCovariance, kProfLinearize, kProfError, kProfGridBuild, kProfDist2, kProfLossFwd, kProfLossBwd, kProfCount
+  kProfCovariance, kProfLinearize, kProfError, kProfGridBuild, kProfDist2, kProfLossFwd, kProfLossBwd, kProfExchange, kProfCount
 };
 extern bool g_prof_on;
 void prof_begin(int k, cudaStream_t s);

@@ -656,23 +656,38 @@ __global__ void moments_compact_kernel(int P, const int32_t* __restrict__ radii,
 }
 
 // Sharded run through the exchange layer (comm.cuh): every rank's render_backward accumulated the moments of ITS tiles in
-// its own segment; after a barrier each rank adds the world's rows of the visible Gaussians in rank order (P2P loads over
-// NVLink, 48 B per visible Gaussian and peer) into its private moments buffer.  No compaction, no host-side count, no
-// host-launched collective.
-__global__ void moments_gather_kernel(CommView c, int P, const int32_t* __restrict__ radii, float* __restrict__ out) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= P || !(radii[i] > 0)) return;
+// its own segment.  The all-reduce over the ranks is two P2P passes over NVLink, both inside our kernels:
+//   reduce-scatter: rank r adds, in rank order, the world's rows of the visible Gaussians of ITS slice of the table
+//                   (slice = ceil(P / world) consecutive Gaussians) into the upper half of its own segment;
+//   all-gather:     every rank copies each visible row from the rank that owns its slice into its private moments buffer.
+// 2 (N-1)/N * 48 B per visible Gaussian cross the links per rank (a one-pass "read everything from everybody" is
+// (N-1) * 48 B: 4x more at 8 ranks).  Every sum is formed once, by one rank, in rank order: identical bits everywhere.
+// No compaction, no host-side count, no host-launched collective.
+__global__ void moments_reduce_slice_kernel(CommView c, int P, int slice, const int32_t* __restrict__ radii, size_t red_off) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = c.rank * slice + k;
+  if (k >= slice || i >= P || !(radii[i] > 0)) return;
   float4 acc[3] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
   for (int r = 0; r < c.world; r++) {
     const float4* src = reinterpret_cast<const float4*>(c.seg[r] + kCommHeapOff) + 3 * (size_t)i;
 #pragma unroll
-    for (int k = 0; k < 3; k++) {
-      const float4 v = __ldcv(src + k);  // written by another GPU since the last read: never from a cached line
-      acc[k].x += v.x; acc[k].y += v.y; acc[k].z += v.z; acc[k].w += v.w;
+    for (int q = 0; q < 3; q++) {
+      const float4 v = __ldcv(src + q);  // written by another GPU since the last read: never from a cached line
+      acc[q].x += v.x; acc[q].y += v.y; acc[q].z += v.z; acc[q].w += v.w;
     }
   }
-  float4* dst = reinterpret_cast<float4*>(out) + 3 * (size_t)i;
+  float4* dst = reinterpret_cast<float4*>(c.seg[c.rank] + kCommHeapOff + red_off) + 3 * (size_t)k;
   dst[0] = acc[0]; dst[1] = acc[1]; dst[2] = acc[2];
+}
+
+__global__ void moments_gather_slices_kernel(CommView c, int P, int slice, const int32_t* __restrict__ radii, size_t red_off,
+                                             float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P || !(radii[i] > 0)) return;
+  const int owner = i / slice, k = i - owner * slice;
+  const float4* src = reinterpret_cast<const float4*>(c.seg[owner] + kCommHeapOff + red_off) + 3 * (size_t)k;
+  float4* dst = reinterpret_cast<float4*>(out) + 3 * (size_t)i;
+  dst[0] = __ldcv(src); dst[1] = __ldcv(src + 1); dst[2] = __ldcv(src + 2);
 }
 
 gsicp_comm* g_raster_comm = nullptr;  // set by gsicp_raster_set_comm; also read by the forward pass (raster_forward.cu)
@@ -840,11 +855,17 @@ extern "C" int gsicp_raster_backward(const gsicp_raster_args* args, int num_rend
 
   float* xmom = nullptr;
   if (comm) {
-    // exchange: barrier (all ranks have finished their render_backward) -> add the world's rows -> barrier (all ranks have
-    // read: the accumulators may be cleared / reused)
+    // exchange: barrier (all ranks have finished their render_backward) -> reduce own slice -> barrier (every slice is
+    // reduced; nobody reads a peer's accumulator any more, so gaussian_backward may clear it) -> gather the slices.  The
+    // reduced slices are overwritten only after the first barrier of the NEXT exchange, which every rank reaches after its
+    // gather in stream order: no third barrier.
+    const int slice = (P + comm->world - 1) / comm->world;
+    const size_t red_off = (comm->heap_bytes() / 2) & ~size_t(255);
+    ProfScope ps_x(kProfExchange, stream);
     if (int e = comm_stream_barrier(comm, stream)) return e;
-    GSICP_LAUNCH(moments_gather_kernel, (P + 255) / 256, 256, 0, stream, comm->view(), P, d_radii, geom.moments);
+    GSICP_LAUNCH(moments_reduce_slice_kernel, (slice + 255) / 256, 256, 0, stream, comm->view(), P, slice, d_radii, red_off);
     if (int e = comm_stream_barrier(comm, stream)) return e;
+    GSICP_LAUNCH(moments_gather_slices_kernel, (P + 255) / 256, 256, 0, stream, comm->view(), P, slice, d_radii, red_off, geom.moments);
     xmom = work;
     work = geom.moments;
   } else if (shard_count > 1 && g_bwd.fn) {

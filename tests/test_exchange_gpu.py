@@ -133,6 +133,15 @@ def test_two_ranks_on_one_gpu_match_single(cuda):
 
 
 if __name__ == "__main__":
+    import time
+
+    t0 = time.time()
+    from gs_icp_slam_b200._lib import check, lib as _l
+
+    torch.cuda.init()
+    torch.zeros(1, device="cuda")
+    check(_l.gsicp_test_preload_kernels(), "gsicp_test_preload_kernels")
+    print("child: CUDA ready after %.1f s (CUDA_MODULE_LOADING=%s)" % (time.time() - t0, os.environ.get("CUDA_MODULE_LOADING", "default")), flush=True)
     for host_lm in (False, True):
         _two_ranks_match_single(host_lm)
-        print("EXCHANGE-OK", host_lm, flush=True)
+        print("EXCHANGE-OK", host_lm, "at %.1f s" % (time.time() - t0), flush=True)
