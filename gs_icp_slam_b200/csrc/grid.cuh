@@ -678,7 +678,7 @@ __device__ __forceinline__ RingCursor block3_slots(const GridView& g, const Grid
   const uint32_t len = e - b;
   uint32_t incl = len;
 #pragma unroll
-  for (int o = 1; o < 16; o <<= 1) {  // only lanes 0..8 hold a slot
+  for (int o = 1; o < 32; o <<= 1) {  // full-width scan: ring_element searches the prefixes of all 32 lanes
     const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
     if (lane >= o) incl += v;
   }

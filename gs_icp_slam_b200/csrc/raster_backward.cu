@@ -90,7 +90,7 @@ render_backward_kernel(const uint32_t* __restrict__ tile_order, const uint2* __r
                        int tiles_x, const float* __restrict__ bg, const Splat* __restrict__ splats,
                        const float* __restrict__ final_T, const uint32_t* __restrict__ n_contrib,
                        const float* __restrict__ dL_dpix_color, const float* __restrict__ dL_dpix_depth,
-                       float* __restrict__ moments, int shard_count, int shard_index) {
+                       float* __restrict__ moments, const uint32_t* __restrict__ hit_in, int shard_count, int shard_index) {
   const int tile = (int)tile_order[blockIdx.x];
   if (shard_count > 1 && (tile % shard_count) != shard_index) return;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -247,8 +247,19 @@ render_backward_kernel(const uint32_t* __restrict__ tile_order, const uint2* __r
   };
   if (total > 0) stage(0, 0);
 
+  // The forward pass recorded, per 32 list positions of the tile and per sub-tile, which instances survive the exact cull
+  // (BinState::hit): replayed here instead of evaluating the cull again.  A batch spans at most kStage / 32 + 1 words;
+  // lane l holds the word of positions 32 (top - l) .. (top = word of the batch's first slot), loaded before the barrier.
+  const uint32_t* const hit_tile = hit_in + hit_word(range.x, tile) * 8 + warp;
+
   for (int base = 0, buf = 0; base < total; base += kStage, buf ^= 1) {
     const int n = min(kStage, total - base);
+    const int p_top = total - 1 - base;  // list position (0-based, front to back) of slot 0 of this batch
+    uint32_t hit_words = 0;
+    if (kCull) {
+      const int w = (p_top >> 5) - lane;
+      if (lane <= kStage / 32 && w >= 0) hit_words = __ldg(hit_tile + (size_t)w * 8);
+    }
     cp_async_wait_all();
     __syncthreads();  // batch `base` is staged; every warp has finished reading the other buffer
     if (base + kStage < total) stage(base + kStage, buf ^ 1);
@@ -262,12 +273,13 @@ render_backward_kernel(const uint32_t* __restrict__ tile_order, const uint2* __r
       uint32_t mask;
       {
         const int j = c0 + lane;
-        bool hit = (j < n) && (first_pos - j <= warp_last);
+        mask = __ballot_sync(0xffffffffu, (j < n) && (first_pos - j <= warp_last));
         if (kCull) {
-          const uint32_t s_j = s_chunk + (uint32_t)(j < n ? lane : 0) * 16u;
-          hit = hit && subtile_hit(lds128<0>(s_j), lds128<kOffB>(s_j), wx0f, wy0f, 7.f, 3.f);
+          // slot c0 + i is list position p_hi - i: bits p_hi - 31 .. p_hi of the recorded masks, reversed
+          const int p_hi = p_top - c0, l1 = (p_top >> 5) - (p_hi >> 5);
+          const uint32_t hi = __shfl_sync(0xffffffffu, hit_words, l1), lo = __shfl_sync(0xffffffffu, hit_words, l1 + 1);
+          mask &= __brev(__funnelshift_rc(lo, hi, (p_hi & 31) + 1));
         }
-        mask = __ballot_sync(0xffffffffu, hit);
       }
       while (mask) {
         const int bit = __ffs(mask) - 1;
@@ -824,7 +836,7 @@ extern "C" int gsicp_raster_backward(const gsicp_raster_args* args, int num_rend
   const int shard_index = shard_count > 1 ? args->tile_shard_index : 0;
   const int tiles_x = (W + kTile - 1) / kTile, tiles_y = (H + kTile - 1) / kTile, tiles = tiles_x * tiles_y;
   GeomState geom = GeomState::from((char*)d_geom, P);
-  BinState bin = BinState::from((char*)d_binning, num_rendered);
+  BinState bin = BinState::from((char*)d_binning, num_rendered, (size_t)tiles);
   ImgState img = ImgState::from((char*)d_image, (size_t)W * H, tiles);
   gsicp_comm* comm = (g_raster_comm && g_raster_comm->world > 1 && shard_count > 1) ? g_raster_comm : nullptr;
   if (comm && (size_t)P * kG * sizeof(float) > comm->heap_bytes() / 2) {
@@ -840,15 +852,15 @@ extern "C" int gsicp_raster_backward(const gsicp_raster_args* args, int num_rend
     if (!g_render_cull) {  // test hook: no sub-tile culling
       GSICP_LAUNCH(render_backward_kernel<false>, tiles, kTilePixels, sizeof(BwdSmem), stream, img.tile_order, img.ranges, bin.point_list,
                    W, H, tiles_x, args->d_background, geom.splats, img.final_T, img.n_contrib, d_dL_dout_color, d_dL_dout_depth,
-                   work, shard_count, shard_index);
+                   work, bin.hit, shard_count, shard_index);
     } else if (g_bwd_variant == 1) {
       GSICP_LAUNCH((render_backward_kernel<true, 128, 4>), tiles, kTilePixels, sizeof(BwdSmemT<128>), stream, img.tile_order, img.ranges,
                    bin.point_list, W, H, tiles_x, args->d_background, geom.splats, img.final_T, img.n_contrib, d_dL_dout_color,
-                   d_dL_dout_depth, work, shard_count, shard_index);
+                   d_dL_dout_depth, work, bin.hit, shard_count, shard_index);
     } else {
       GSICP_LAUNCH(render_backward_kernel<true>, tiles, kTilePixels, sizeof(BwdSmem), stream, img.tile_order, img.ranges, bin.point_list,
                    W, H, tiles_x, args->d_background, geom.splats, img.final_T, img.n_contrib, d_dL_dout_color, d_dL_dout_depth,
-                   work, shard_count, shard_index);
+                   work, bin.hit, shard_count, shard_index);
     }
     if (args->debug) GSICP_CUDA(cudaStreamSynchronize(stream));
   }

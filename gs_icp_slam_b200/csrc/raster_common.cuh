@@ -239,15 +239,22 @@ struct GeomState {   // kept for backward: 97 B / Gaussian
   }
 };
 
-struct BinState {        // kept for backward: 4 B / tile instance
+struct BinState {        // kept for backward: 5 B / tile instance
   uint32_t* point_list;  // [R] Gaussian index per tile instance, sorted by (tile, depth, index)
-  static size_t bytes(size_t R) { return 128 + (R ? R : 1) * sizeof(uint32_t); }
-  static BinState from(char* p, size_t R) {
+  // Sub-tile hit masks of the forward pass: for tile t, chunk c (list positions 32 c .. 32 c + 31 of the tile) and warp w
+  // (the 8x4 sub-tile), bit i of hit[(hit_word(range.x, t) + c) * 8 + w] says whether instance 32 c + i survived the exact
+  // sub-tile cull.  render_backward replays them instead of culling again.  Consecutive tiles never share a word.
+  uint32_t* hit;
+  static size_t hit_words(size_t R, size_t tiles) { return ((R >> 5) + tiles + 2) * 8; }
+  static size_t bytes(size_t R, size_t tiles) { return 2 * 128 + (R ? R : 1) * sizeof(uint32_t) + hit_words(R, tiles) * sizeof(uint32_t); }
+  static BinState from(char* p, size_t R, size_t tiles) {
     BinState b;
     b.point_list = carve<uint32_t>(p, R ? R : 1);
+    b.hit = carve<uint32_t>(p, hit_words(R, tiles));
     return b;
   }
 };
+__host__ __device__ __forceinline__ size_t hit_word(uint32_t range_begin, int tile) { return (size_t)(range_begin >> 5) + (size_t)tile; }
 
 struct ImgState {       // kept for backward: 8 B / pixel + 8 B / tile
   float* final_T;       // [N] transmittance after the last blended Gaussian (T == T_d)

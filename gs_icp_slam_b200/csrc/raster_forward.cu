@@ -335,7 +335,7 @@ render_forward_kernel(const uint32_t* __restrict__ tile_order, const uint2* __re
                       const uint32_t* __restrict__ point_list, int W, int H,
                       int tiles_x, const Splat* __restrict__ splats, const float* __restrict__ bg,
                       float* __restrict__ out_color, float* __restrict__ out_depth, float* __restrict__ final_T,
-                      uint32_t* __restrict__ n_contrib, int shard_count, int shard_index) {
+                      uint32_t* __restrict__ n_contrib, uint32_t* __restrict__ hit_out, int shard_count, int shard_index) {
   const int tile = (int)tile_order[blockIdx.x];
   if (shard_count > 1 && (tile % shard_count) != shard_index) return;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -388,6 +388,8 @@ render_forward_kernel(const uint32_t* __restrict__ tile_order, const uint2* __re
       } else {
         mask = (n - c0 >= 32) ? 0xffffffffu : ((1u << (n - c0)) - 1u);
       }
+      // kept for the backward pass (BinState::hit): every chunk this warp evaluates reaches at least its last contributor
+      if (lane == 0) hit_out[(hit_word(range.x, tile) + (size_t)((base + c0) >> 5)) * 8 + warp] = mask;
       while (mask) {
         const int bit = __ffs(mask) - 1;
         mask &= mask - 1;
@@ -593,12 +595,12 @@ extern "C" int gsicp_raster_forward(const gsicp_raster_args* args, float* d_out_
     GSICP_CUDA(cudaMemsetAsync(img.ranges, 0, sizeof(uint2) * tiles, stream));
   }
 
-  char* bin_p = (char*)binning_alloc(BinState::bytes(R), user);
+  char* bin_p = (char*)binning_alloc(BinState::bytes(R, (size_t)tiles), user);
   if (!bin_p) {
     set_error("gsicp_raster_forward: binning callback returned NULL");
     return GSICP_ENOMEM;
   }
-  BinState bin = BinState::from(bin_p, R);
+  BinState bin = BinState::from(bin_p, R, (size_t)tiles);
 
   if (R > 0) {
     const size_t kbytes = ((size_t)R * 8 + 127) & ~size_t(127);
@@ -649,11 +651,11 @@ extern "C" int gsicp_raster_forward(const gsicp_raster_args* args, float* d_out_
     ProfScope ps(kProfRenderFwd, stream);
     if (g_render_cull) {
       GSICP_LAUNCH(render_forward_kernel<true>, tiles, kTilePixels, 0, stream, img.tile_order, img.ranges, bin.point_list, W, H, tiles_x,
-                   geom.splats, args->d_background, d_out_color, d_out_depth, img.final_T, img.n_contrib, shard_count,
+                   geom.splats, args->d_background, d_out_color, d_out_depth, img.final_T, img.n_contrib, bin.hit, shard_count,
                    shard_index);
     } else {
       GSICP_LAUNCH(render_forward_kernel<false>, tiles, kTilePixels, 0, stream, img.tile_order, img.ranges, bin.point_list, W, H, tiles_x,
-                   geom.splats, args->d_background, d_out_color, d_out_depth, img.final_T, img.n_contrib, shard_count,
+                   geom.splats, args->d_background, d_out_color, d_out_depth, img.final_T, img.n_contrib, bin.hit, shard_count,
                    shard_index);
     }
     if (args->debug) GSICP_CUDA(cudaStreamSynchronize(stream));
@@ -669,7 +671,7 @@ extern "C" int gsicp_raster_export_binning(const gsicp_raster_args* args, int nu
   cudaStream_t stream = (cudaStream_t)stream_v;
   const int W = args->width, H = args->height;
   const int tiles_x = (W + kTile - 1) / kTile, tiles_y = (H + kTile - 1) / kTile, tiles = tiles_x * tiles_y;
-  BinState bin = BinState::from((char*)d_binning, num_rendered);
+  BinState bin = BinState::from((char*)d_binning, num_rendered, (size_t)tiles);
   ImgState img = ImgState::from((char*)d_image, (size_t)W * H, tiles);
   if (d_point_list && num_rendered > 0)
     GSICP_CUDA(cudaMemcpyAsync(d_point_list, bin.point_list, sizeof(uint32_t) * (size_t)num_rendered,

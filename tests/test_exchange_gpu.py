@@ -6,8 +6,9 @@ getters.  The real multi-process / NVLink path is tests/test_multigpu_gpu.py (ne
 
 Two ranks sharing ONE CUDA context is an emulation with a hazard the real layout (one process and one context per GPU)
 does not have: anything that synchronises the whole context while a peer's kernel spins on a flag deadlocks — lazy module
-loading of a kernel's first launch does, and so does cudaFree/cudaHostAlloc.  So the ranks run in a child process with
-CUDA_MODULE_LOADING=EAGER, and every handle does one unsharded pass first (all scratch sized, nothing left to allocate)."""
+loading of a kernel's first launch does, and so does cudaFree/cudaHostAlloc.  So the ranks run in a child process that loads
+the library's kernels up front (gsicp_test_preload_kernels), and every handle does one unsharded pass first (all scratch
+sized, nothing left to allocate, every PyTorch kernel on the call path loaded)."""
 import ctypes as C
 import os
 import subprocess
@@ -51,7 +52,7 @@ def _run_ranks(world, fn):
     for t in th:
         t.start()
     for t in th:
-        t.join(timeout=200)
+        t.join(timeout=100)
     for e in err:
         if e is not None:
             raise e
@@ -124,11 +125,11 @@ def _two_ranks_match_single(host_lm):
 
 def test_two_ranks_on_one_gpu_match_single(cuda):
     """Both LM drivers (persistent kernel with in-kernel exchange; host-driven kernels with the exchange in the last block) in
-    ONE child process: eager module loading costs about a minute of start-up."""
-    env = dict(os.environ, CUDA_MODULE_LOADING="EAGER")
+    ONE child process (a hang there cannot take the pytest process and its CUDA context with it)."""
+    env = dict(os.environ)
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     env["PYTHONPATH"] = root + os.pathsep + env.get("PYTHONPATH", "")
-    p = subprocess.run([sys.executable, os.path.abspath(__file__)], env=env, cwd=root, capture_output=True, text=True, timeout=280)
+    p = subprocess.run([sys.executable, os.path.abspath(__file__)], env=env, cwd=root, capture_output=True, text=True, timeout=150)
     assert p.returncode == 0 and "EXCHANGE-OK False" in p.stdout and "EXCHANGE-OK True" in p.stdout, p.stdout[-2000:] + p.stderr[-4000:]
 
 
