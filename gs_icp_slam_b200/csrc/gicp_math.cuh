@@ -248,59 +248,98 @@ GM_HD void gm_swap(double& a, double& b) {
 // Pivoted LDL^T of a symmetric 6x6 and solve, following Eigen's LDLT (Eigen/src/Cholesky/LDLT.h:
 // unblocked lower factorisation with diagonal pivoting, then P^T L^-T D^-1 L^-1 P b).
 GM_HD void ldlt_solve6(const double Hin[6][6], const double rhs[6], double x[6]) {
-  const int n = 6;
+  // Every loop below has compile-time bounds once the k loop is unrolled and the pivot row is matched against the static
+  // candidates p = k+1..5, so on the device the whole factorisation lives in registers (no local-memory arrays with
+  // run-time indices): the LM decision is a serial section of align_lm_kernel.  Same operations in the same order as the
+  // plain triple loop.
+  constexpr int n = 6;
   double A[6][6];
   int tr[6];
+#pragma unroll
   for (int i = 0; i < n; i++)
+#pragma unroll
     for (int j = 0; j < n; j++) A[i][j] = Hin[i][j];
+  bool stop = false;
+#pragma unroll
   for (int k = 0; k < n; k++) {
+    if (stop) {
+      continue;
+    }
     int piv = k;
     double big = fabs(A[k][k]);
+#pragma unroll
     for (int i = k + 1; i < n; i++)
       if (fabs(A[i][i]) > big) {
         big = fabs(A[i][i]);
         piv = i;
       }
     tr[k] = piv;
-    if (piv != k) {  // symmetric row/column interchange on the lower triangle
-      const int s = n - piv - 1;
-      for (int c = 0; c < k; c++) gm_swap(A[k][c], A[piv][c]);
-      for (int r = 0; r < s; r++) gm_swap(A[piv + 1 + r][k], A[piv + 1 + r][piv]);
-      gm_swap(A[k][k], A[piv][piv]);
-      for (int i = k + 1; i < piv; i++) gm_swap(A[i][k], A[piv][i]);
+#pragma unroll
+    for (int p = k + 1; p < n; p++) {
+      if (piv == p) {  // symmetric row/column interchange on the lower triangle
+#pragma unroll
+        for (int c = 0; c < k; c++) gm_swap(A[k][c], A[p][c]);
+#pragma unroll
+        for (int r = p + 1; r < n; r++) gm_swap(A[r][k], A[r][p]);
+        gm_swap(A[k][k], A[p][p]);
+#pragma unroll
+        for (int i = k + 1; i < p; i++) gm_swap(A[i][k], A[p][i]);
+      }
     }
-    const int rs = n - k - 1;
     if (k > 0) {
       double temp[6];
+#pragma unroll
       for (int c = 0; c < k; c++) temp[c] = A[c][c] * A[k][c];
       double acc = 0.0;
+#pragma unroll
       for (int c = 0; c < k; c++) acc += A[k][c] * temp[c];
       A[k][k] -= acc;
-      for (int r = 0; r < rs; r++) {
+#pragma unroll
+      for (int r = k + 1; r < n; r++) {
         double a2 = 0.0;
-        for (int c = 0; c < k; c++) a2 += A[k + 1 + r][c] * temp[c];
-        A[k + 1 + r][k] -= a2;
+#pragma unroll
+        for (int c = 0; c < k; c++) a2 += A[r][c] * temp[c];
+        A[r][k] -= a2;
       }
     }
     const double akk = A[k][k];
     const bool valid = fabs(akk) > 0.0;
     if (k == 0 && !valid) {
+#pragma unroll
       for (int j = 0; j < n; j++) tr[j] = j;
-      break;
+      stop = true;
+    } else if (valid) {
+#pragma unroll
+      for (int r = k + 1; r < n; r++) A[r][k] /= akk;
     }
-    if (rs > 0 && valid)
-      for (int r = 0; r < rs; r++) A[k + 1 + r][k] /= akk;
   }
   double y[6];
+#pragma unroll
   for (int i = 0; i < n; i++) y[i] = rhs[i];
-  for (int k = 0; k < n; k++) gm_swap(y[k], y[tr[k]]);           // P b
+#pragma unroll
+  for (int k = 0; k < n; k++) {                                    // P b
+#pragma unroll
+    for (int p = k + 1; p < n; p++)
+      if (tr[k] == p) gm_swap(y[k], y[p]);
+  }
+#pragma unroll
   for (int i = 0; i < n; i++)                                      // L^-1
+#pragma unroll
     for (int c = 0; c < i; c++) y[i] -= A[i][c] * y[c];
   const double tol = 1.0 / DBL_MAX;
+#pragma unroll
   for (int i = 0; i < n; i++) y[i] = (fabs(A[i][i]) > tol) ? y[i] / A[i][i] : 0.0;  // D^-1
+#pragma unroll
   for (int i = n - 1; i >= 0; i--)                                 // L^-T
+#pragma unroll
     for (int c = i + 1; c < n; c++) y[i] -= A[c][i] * y[c];
-  for (int k = n - 1; k >= 0; k--) gm_swap(y[k], y[tr[k]]);      // P^T
+#pragma unroll
+  for (int k = n - 1; k >= 0; k--) {                               // P^T
+#pragma unroll
+    for (int p = k + 1; p < n; p++)
+      if (tr[k] == p) gm_swap(y[k], y[p]);
+  }
+#pragma unroll
   for (int i = 0; i < n; i++) x[i] = y[i];
 }
 

@@ -631,9 +631,10 @@ gaussian_backward_kernel(BwdArgs a, const int32_t* __restrict__ radii, const uin
 }
 
 extern int g_render_cull;
-// 1 (default): 128-entry staging, 64 registers, 4 CTAs/SM; 0: 256-entry staging, 3 CTAs/SM (r2e: 222.5 vs 227.0 us at C3,
-// 1103 vs 1203 us at C4).  Same arithmetic per survivor; the switch exists for tools/bench_raster.py and the parity tests.
-int g_bwd_variant = [] { const char* e = getenv("GSICP_BWD_VARIANT"); return e ? atoi(e) : 1; }();
+// 0 (default): 256-entry staging, 80 registers, 3 CTAs/SM; 1: 128-entry staging, 64 registers, 4 CTAs/SM.  Measured (r2j, with
+// the recorded hit masks): 176.2 vs 185.5 us at C3, 912 vs 930 us at C4 — fewer, longer batches win once the cull is gone.
+// Same arithmetic per survivor; the switch exists for tools/bench_raster.py and the parity tests.
+int g_bwd_variant = [] { const char* e = getenv("GSICP_BWD_VARIANT"); return e ? atoi(e) : 0; }();
 
 // ---- multi-GPU: all-reduce of the render moments of the VISIBLE Gaussians ----
 // Every rank preprocesses all Gaussians, so the set {radii > 0} and its index order are identical on all ranks: the

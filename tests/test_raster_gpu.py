@@ -402,8 +402,8 @@ def test_autograd_vs_reference_torch_extension(cuda, P, size, degree, seed):
 
 @pytest.mark.parametrize("variant", [0, 1])
 def test_backward_staging_variants_vs_reference_extension(cuda, variant):
-    """render_backward_kernel ships in two launch configurations (256-entry staging / 3 CTAs per SM and 128-entry staging /
-    4 CTAs per SM, the default).  Each one must match the reference extension's gradients on its own."""
+    """render_backward_kernel ships in two launch configurations (256-entry staging / 3 CTAs per SM, the default, and 128-entry
+    staging / 4 CTAs per SM).  Each one must match the reference extension's gradients on its own."""
     from gs_icp_slam_b200 import _lib
     from oracle import ref_ext
 
@@ -413,4 +413,4 @@ def test_backward_staging_variants_vs_reference_extension(cuda, variant):
     try:
         test_autograd_vs_reference_torch_extension(cuda, 100000, (640, 480), 0, 3)
     finally:
-        _lib.lib.gsicp_test_set_bwd_variant(1)
+        _lib.lib.gsicp_test_set_bwd_variant(0)

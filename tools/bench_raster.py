@@ -54,4 +54,4 @@ for v in (0, 1):
     _lib.prof_enable(False)
     k = {n: round(ms / cnt * 1e3, 1) for n, (ms, cnt) in _lib.prof_read().items() if cnt}
     print(f"{which} variant {v}: render_backward {k.get('render_backward')} us   all: {k}", flush=True)
-_lib.lib.gsicp_test_set_bwd_variant(1)
+_lib.lib.gsicp_test_set_bwd_variant(0)
