@@ -1,6 +1,6 @@
 #!/bin/bash
 # 8-GPU batch (gpurun --gpus 8): sharding parity (2 ranks), strong scaling of the large configs at 1/2/4/8, replicas at 8.
-TAG=${1:-r2k}
+TAG=${1:-multi}
 mkdir -p gpurun_out
 step() { local t0=$(date +%s); local lim=$1; shift; timeout $lim "$@"; local rc=$?; echo "[step rc=$rc $(( $(date +%s) - t0 ))s] $*" | cut -c1-200; }
 TR="python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1"
