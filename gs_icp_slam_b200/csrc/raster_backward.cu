@@ -247,8 +247,8 @@ render_backward_kernel(const uint32_t* __restrict__ tile_order, const uint2* __r
   };
   if (total > 0) stage(0, 0);
 
-  // The forward pass recorded, per 32 list positions of the tile and per sub-tile, which instances survive the exact cull
-  // (BinState::hit): replayed here instead of evaluating the cull again.  A batch spans at most kStage / 32 + 1 words;
+  // The forward pass recorded, per 32 list positions of the tile and per sub-tile, which instances at least one pixel blended
+  // (BinState::hit): exactly the instances the replay has to visit — no cull and no "did anybody blend it" vote here.  A batch spans at most kStage / 32 + 1 words;
   // lane l holds the word of positions 32 (top - l) .. (top = word of the batch's first slot), loaded before the barrier.
   const uint32_t* const hit_tile = hit_in + hit_word(range.x, tile) * 8 + warp;
 
@@ -271,15 +271,16 @@ render_backward_kernel(const uint32_t* __restrict__ tile_order, const uint2* __r
       uint32_t s_chunk = s_base + (uint32_t)(buf * kStage + c0) * 16u;  // sm.a[buf][c0]
       asm volatile("" : "+r"(s_chunk));  // opaque: keep it in a register instead of rebuilding it per survivor
       uint32_t mask;
-      {
+      if (kCull) {
+        // slot c0 + i is list position p_hi - i: bits p_hi - 31 .. p_hi of the recorded masks, reversed.  A blended instance
+        // lies at or before the warp's last contributor by construction; only the slots past the end of the list are cut.
+        const int p_hi = p_top - c0, l1 = (p_top >> 5) - (p_hi >> 5);
+        const uint32_t hi = __shfl_sync(0xffffffffu, hit_words, l1), lo = __shfl_sync(0xffffffffu, hit_words, l1 + 1);
+        mask = __brev(__funnelshift_rc(lo, hi, (p_hi & 31) + 1));
+        if (n - c0 < 32) mask &= (1u << (n - c0)) - 1u;
+      } else {
         const int j = c0 + lane;
         mask = __ballot_sync(0xffffffffu, (j < n) && (first_pos - j <= warp_last));
-        if (kCull) {
-          // slot c0 + i is list position p_hi - i: bits p_hi - 31 .. p_hi of the recorded masks, reversed
-          const int p_hi = p_top - c0, l1 = (p_top >> 5) - (p_hi >> 5);
-          const uint32_t hi = __shfl_sync(0xffffffffu, hit_words, l1), lo = __shfl_sync(0xffffffffu, hit_words, l1 + 1);
-          mask &= __brev(__funnelshift_rc(lo, hi, (p_hi & 31) + 1));
-        }
       }
       while (mask) {
         const int bit = __ffs(mask) - 1;
@@ -294,7 +295,7 @@ render_backward_kernel(const uint32_t* __restrict__ tile_order, const uint2* __r
         const float alpha = fminf(0.99f, b.y * G);
         const bool active = inside && (contributor <= last_contributor) && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
 
-        if (!__any_sync(0xffffffffu, active)) continue;  // no pixel of this sub-tile blended the instance
+        if (!kCull && !__any_sync(0xffffffffu, active)) continue;  // (with the recorded masks every visited instance was blended)
 
         float tq = 0.f, wq = 0.f;
         if (active) {
