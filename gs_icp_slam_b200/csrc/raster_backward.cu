@@ -247,8 +247,8 @@ render_backward_kernel(const uint32_t* __restrict__ tile_order, const uint2* __r
   };
   if (total > 0) stage(0, 0);
 
-  // The forward pass recorded, per 32 list positions of the tile and per sub-tile, which instances at least one pixel blended
-  // (BinState::hit): exactly the instances the replay has to visit — no cull and no "did anybody blend it" vote here.  A batch spans at most kStage / 32 + 1 words;
+  // The forward pass recorded, per 32 list positions of the tile and per sub-tile, which instances survive the exact cull
+  // (BinState::hit): replayed here instead of evaluating the cull again.  A batch spans at most kStage / 32 + 1 words;
   // lane l holds the word of positions 32 (top - l) .. (top = word of the batch's first slot), loaded before the barrier.
   const uint32_t* const hit_tile = hit_in + hit_word(range.x, tile) * 8 + warp;
 
@@ -271,16 +271,15 @@ render_backward_kernel(const uint32_t* __restrict__ tile_order, const uint2* __r
       uint32_t s_chunk = s_base + (uint32_t)(buf * kStage + c0) * 16u;  // sm.a[buf][c0]
       asm volatile("" : "+r"(s_chunk));  // opaque: keep it in a register instead of rebuilding it per survivor
       uint32_t mask;
-      if (kCull) {
-        // slot c0 + i is list position p_hi - i: bits p_hi - 31 .. p_hi of the recorded masks, reversed.  A blended instance
-        // lies at or before the warp's last contributor by construction; only the slots past the end of the list are cut.
-        const int p_hi = p_top - c0, l1 = (p_top >> 5) - (p_hi >> 5);
-        const uint32_t hi = __shfl_sync(0xffffffffu, hit_words, l1), lo = __shfl_sync(0xffffffffu, hit_words, l1 + 1);
-        mask = __brev(__funnelshift_rc(lo, hi, (p_hi & 31) + 1));
-        if (n - c0 < 32) mask &= (1u << (n - c0)) - 1u;
-      } else {
+      {
         const int j = c0 + lane;
         mask = __ballot_sync(0xffffffffu, (j < n) && (first_pos - j <= warp_last));
+        if (kCull) {
+          // slot c0 + i is list position p_hi - i: bits p_hi - 31 .. p_hi of the recorded masks, reversed
+          const int p_hi = p_top - c0, l1 = (p_top >> 5) - (p_hi >> 5);
+          const uint32_t hi = __shfl_sync(0xffffffffu, hit_words, l1), lo = __shfl_sync(0xffffffffu, hit_words, l1 + 1);
+          mask &= __brev(__funnelshift_rc(lo, hi, (p_hi & 31) + 1));
+        }
       }
       while (mask) {
         const int bit = __ffs(mask) - 1;
@@ -295,7 +294,7 @@ render_backward_kernel(const uint32_t* __restrict__ tile_order, const uint2* __r
         const float alpha = fminf(0.99f, b.y * G);
         const bool active = inside && (contributor <= last_contributor) && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
 
-        if (!kCull && !__any_sync(0xffffffffu, active)) continue;  // (with the recorded masks every visited instance was blended)
+        if (!__any_sync(0xffffffffu, active)) continue;  // no pixel of this sub-tile blended the instance
 
         float tq = 0.f, wq = 0.f;
         if (active) {
@@ -414,6 +413,18 @@ __device__ __forceinline__ F3 sh_backward(int idx, const BwdArgs& a, uint8_t cla
   return dnormv(dir_orig, dL_ddir);
 }
 
+// Clears rows [wbase, wbase + 32) of a row-major [P][k] float array with one warp: 128-bit stores when the block is 16-byte
+// aligned (always, for 16-byte aligned arrays: the block starts 128 k bytes into the array), 32-bit coalesced stores otherwise.
+__device__ __forceinline__ void zero_rows(float* __restrict__ out, int k, int wbase, int lane) {
+  float* base = out + (size_t)wbase * k;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) == 0) {
+    float4* b4 = reinterpret_cast<float4*>(base);
+    for (int i = lane; i < 8 * k; i += 32) b4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  } else {
+    for (int i = lane; i < 32 * k; i += 32) base[i] = 0.f;
+  }
+}
+
 __global__ void __launch_bounds__(256)
 gaussian_backward_kernel(BwdArgs a, const int32_t* __restrict__ radii, const uint8_t* __restrict__ clamped,
                          float* __restrict__ moments, const Splat* __restrict__ splats, int W, int H,
@@ -422,29 +433,46 @@ gaussian_backward_kernel(BwdArgs a, const int32_t* __restrict__ radii, const uin
                          float* __restrict__ dL_dcov3D, float* __restrict__ dL_dsh, float* __restrict__ dL_dscales,
                          float* __restrict__ dL_drots, float* __restrict__ xmom) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  // Every gradient row of an invisible Gaussian is exactly zero, and the kernel writes those zeros itself: the caller hands
+  // over uninitialised memory and no P-sized fill launch precedes the backward (the reference zero-fills ten tensors,
+  // rasterize_points.cu:158-167).  89 % of the rows are such rows, so a warp first clears the 32-row block of every output
+  // with coalesced (128-bit where aligned) stores; the visible lanes then overwrite their own rows.
+  const int lane = threadIdx.x & 31;
+  const int wbase = idx - lane;
+  const bool full = wbase + 32 <= a.P;  // warp-uniform; the last, partial warp takes the per-row path
+  if (full) {
+    zero_rows(dL_dmean2D, 3, wbase, lane);
+    zero_rows(dL_dcolors, 3, wbase, lane);
+    zero_rows(dL_dopacity, 1, wbase, lane);
+    zero_rows(dL_dmeans3D, 3, wbase, lane);
+    zero_rows(dL_dcov3D, 6, wbase, lane);
+    if (dL_dsh) zero_rows(dL_dsh, 3 * a.M, wbase, lane);
+    zero_rows(dL_dscales, 3, wbase, lane);
+    zero_rows(dL_drots, 4, wbase, lane);
+    __syncwarp();  // orders the block clear before the visible lanes' own stores
+  }
   if (idx >= a.P) return;
-  // dL_dmean2D is [P][3]; the third component is never written by the reference either (stays zero)
-  dL_dmean2D[3 * (size_t)idx + 2] = 0.f;
   if (!(radii[idx] > 0)) {
-    // Invisible Gaussian: every gradient row is exactly zero.  The kernel writes the zeros itself, so the caller hands
-    // over uninitialised memory: no P-sized fill launch precedes the backward (the reference zero-fills ten tensors,
-    // rasterize_points.cu:158-167).
-    dL_dmean2D[3 * (size_t)idx + 0] = 0.f;
-    dL_dmean2D[3 * (size_t)idx + 1] = 0.f;
+    if (!full) {
 #pragma unroll
-    for (int i = 0; i < 3; i++) {
-      dL_dcolors[3 * (size_t)idx + i] = 0.f;
-      dL_dmeans3D[3 * (size_t)idx + i] = 0.f;
-      dL_dscales[3 * (size_t)idx + i] = 0.f;
+      for (int i = 0; i < 3; i++) {
+        dL_dmean2D[3 * (size_t)idx + i] = 0.f;
+        dL_dcolors[3 * (size_t)idx + i] = 0.f;
+        dL_dmeans3D[3 * (size_t)idx + i] = 0.f;
+        dL_dscales[3 * (size_t)idx + i] = 0.f;
+      }
+      dL_dopacity[idx] = 0.f;
+#pragma unroll
+      for (int i = 0; i < 6; i++) dL_dcov3D[6 * (size_t)idx + i] = 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; i++) dL_drots[4 * (size_t)idx + i] = 0.f;
+      if (dL_dsh)
+        for (int i = 0; i < 3 * a.M; i++) dL_dsh[(size_t)idx * 3 * a.M + i] = 0.f;
     }
-    dL_dopacity[idx] = 0.f;
-#pragma unroll
-    for (int i = 0; i < 6; i++) dL_dcov3D[6 * (size_t)idx + i] = 0.f;
-    reinterpret_cast<float4*>(dL_drots)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (dL_dsh)
-      for (int i = 0; i < 3 * a.M; i++) dL_dsh[(size_t)idx * 3 * a.M + i] = 0.f;
     return;
   }
+  // dL_dmean2D is [P][3]; the third component is never written by the reference either (stays zero)
+  dL_dmean2D[3 * (size_t)idx + 2] = 0.f;
 
   const float3 mean = make_float3(a.means[3 * idx], a.means[3 * idx + 1], a.means[3 * idx + 2]);
   float cov3[6];

@@ -242,9 +242,8 @@ struct GeomState {   // kept for backward: 97 B / Gaussian
 struct BinState {        // kept for backward: 5 B / tile instance
   uint32_t* point_list;  // [R] Gaussian index per tile instance, sorted by (tile, depth, index)
   // Sub-tile hit masks of the forward pass: for tile t, chunk c (list positions 32 c .. 32 c + 31 of the tile) and warp w
-  // (the 8x4 sub-tile), bit i of hit[(hit_word(range.x, t) + c) * 8 + w] says whether at least one pixel of the sub-tile
-  // blended instance 32 c + i (it survived the exact cull AND some pixel's alpha test).  render_backward visits exactly
-  // these instead of culling and testing again.  Consecutive tiles never share a word.
+  // (the 8x4 sub-tile), bit i of hit[(hit_word(range.x, t) + c) * 8 + w] says whether instance 32 c + i survived the exact
+  // sub-tile cull.  render_backward replays them instead of culling again.  Consecutive tiles never share a word.
   uint32_t* hit;
   static size_t hit_words(size_t R, size_t tiles) { return ((R >> 5) + tiles + 2) * 8; }
   static size_t bytes(size_t R, size_t tiles) { return 2 * 128 + (R ? R : 1) * sizeof(uint32_t) + hit_words(R, tiles) * sizeof(uint32_t); }

@@ -388,7 +388,8 @@ render_forward_kernel(const uint32_t* __restrict__ tile_order, const uint2* __re
       } else {
         mask = (n - c0 >= 32) ? 0xffffffffu : ((1u << (n - c0)) - 1u);
       }
-      uint32_t blended = 0;  // instances of this chunk that at least one pixel of the sub-tile blended
+      // kept for the backward pass (BinState::hit): every chunk this warp evaluates reaches at least its last contributor
+      if (lane == 0) hit_out[(hit_word(range.x, tile) + (size_t)((base + c0) >> 5)) * 8 + warp] = mask;
       while (mask) {
         const int bit = __ffs(mask) - 1;
         mask &= mask - 1;
@@ -411,11 +412,7 @@ render_forward_kernel(const uint32_t* __restrict__ tile_order, const uint2* __re
         D = blend ? (D + dcond * alpha * T) : D;
         T = blend ? test_T : T;
         last = blend ? (uint32_t)(base + j + 1) : last;
-        if (__any_sync(0xffffffffu, blend)) blended |= 1u << bit;
       }
-      // kept for the backward pass (BinState::hit): a pixel's backward replay touches exactly the instances it blended, so
-      // the backward visits only these (every chunk this warp evaluates reaches at least its last contributor)
-      if (lane == 0) hit_out[(hit_word(range.x, tile) + (size_t)((base + c0) >> 5)) * 8 + warp] = blended;
       if (__all_sync(0xffffffffu, done)) break;
     }
   }
