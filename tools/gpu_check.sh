@@ -9,4 +9,4 @@ step 120 python tools/bench_raster.py c4 2>&1 | tee gpurun_out/bench_raster_c4_$
 step 60 python tools/prof_align.py 3 2>&1 | tail -4 | cut -c1-300
 step 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/bench_20_$TAG.log 2>&1
 python tools/parse_bench.py gpurun_out/bench_20_$TAG.log
-step 300 ncu --set full --clock-control none --import-source on -k regex:"render_backward|render_forward|gaussian_backward" -s 6 -c 6 -o gpurun_out/prof_$TAG python tools/prof_frame.py 3 > gpurun_out/prof_$TAG.log 2>&1
+[ "${NCU:-1}" = "1" ] && step 300 ncu --set full --clock-control none --import-source on -k regex:"render_backward|render_forward|gaussian_backward" -s 6 -c 6 -o gpurun_out/prof_$TAG python tools/prof_frame.py 3 > gpurun_out/prof_$TAG.log 2>&1
