@@ -273,49 +273,10 @@ emit_binned_kernel(int P, const uint32_t* __restrict__ tiles_touched, const Spla
     key = ((unsigned long long)__float_as_uint(sp->c.w) << 32) | (unsigned long long)(uint32_t)g;
     tile_rect(a.x, a.y, radii[g], tiles_x, tiles_y, x0, y0, x1, y1);
   }
-  // The slot of a key is the RETURN value of an atomic (about a microsecond away in L2), and a loop that stores right after
-  // each atomic exposes that latency once per visible Gaussian (ncu r2m: 36 warps stalled on the scoreboard per issue).  So the
-  // visible Gaussians of the warp are taken four at a time: the first-round atomics of all four are issued, then the four
-  // stores.  Rectangles above 32 tiles finish their further rounds on the spot.
-  const int lane = threadIdx.x & 31;
-  unsigned m = __ballot_sync(0xffffffffu, vis);
-  auto take = [&](uint32_t& slot, unsigned long long& kq, bool& has) {  // next visible Gaussian of the warp, if any
-    has = false;
-    slot = 0;
-    kq = 0;
-    if (!m) return;  // warp-uniform
-    const int src = __ffs(m) - 1;
-    m &= m - 1;
-    const int rx0 = __shfl_sync(0xffffffffu, x0, src), ry0 = __shfl_sync(0xffffffffu, y0, src);
-    const int rx1 = __shfl_sync(0xffffffffu, x1, src), ry1 = __shfl_sync(0xffffffffu, y1, src);
-    kq = __shfl_sync(0xffffffffu, key, src);
-    const int w = rx1 - rx0, n = w * (ry1 - ry0);
-    if (lane < n) {
-      const int t = (ry0 + lane / w) * tiles_x + rx0 + lane % w;
-      if (!(shard_count > 1 && (t % shard_count) != shard_index)) {
-        has = true;
-        slot = atomicAdd(&cursor[t], 1u);
-      }
-    }
-    for (int k = lane + 32; k < n; k += 32) {
-      const int t = (ry0 + k / w) * tiles_x + rx0 + k % w;
-      if (shard_count > 1 && (t % shard_count) != shard_index) continue;
-      keys[atomicAdd(&cursor[t], 1u)] = kq;
-    }
-  };
-  while (m) {
-    uint32_t s0, s1, s2, s3;
-    unsigned long long k0, k1, k2, k3;
-    bool h0, h1, h2, h3;
-    take(s0, k0, h0);
-    take(s1, k1, h1);
-    take(s2, k2, h2);
-    take(s3, k3, h3);
-    if (h0) keys[s0] = k0;
-    if (h1) keys[s1] = k1;
-    if (h2) keys[s2] = k2;
-    if (h3) keys[s3] = k3;
-  }
+  // (Measured and dropped, r2p: keeping the slot atomics of four Gaussians in flight before the dependent key stores did
+  // not shorten the kernel — it waits on the gathered splat / radius loads, not on the atomics' return values.)
+  for_each_owned_tile(vis, x0, y0, x1, y1, tiles_x, shard_count, shard_index, key,
+                      [&](unsigned long long k, int t) { keys[atomicAdd(&cursor[t], 1u)] = k; });
 }
 
 // One CTA per tile: bitonic sort of the tile's keys in shared memory, ids written to point_list.  CTA b sorts tile
