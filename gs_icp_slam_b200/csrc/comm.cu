@@ -35,8 +35,13 @@ int comm_preload_kernels() {
 
 int comm_stream_barrier(gsicp_comm* c, cudaStream_t stream) {
   if (!c || !c->connected || c->world <= 1) return GSICP_OK;
+  if (c->h_status && *(volatile int*)c->h_status) {
+    set_error("exchange group (rank %d of %d): an earlier barrier ran out of its poll budget - a peer did not arrive; results since "
+              "then are not valid", c->rank, c->world);
+    return GSICP_ECUDA;
+  }
   const unsigned long long seq = ++c->bar_seq;
-  GSICP_LAUNCH(comm_barrier_kernel, 1, 32, 0, stream, c->view(), seq, (int*)nullptr);
+  GSICP_LAUNCH(comm_barrier_kernel, 1, 32, 0, stream, c->view(), seq, c->d_status);
   GSICP_CUDA(cudaGetLastError());
   return GSICP_OK;
 }
@@ -49,22 +54,23 @@ extern "C" int gsicp_comm_alloc(size_t heap_bytes, gsicp_comm** out, void* handl
   if (!out || !handle64) return GSICP_EINVAL;
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
   gsicp_comm* c = new gsicp_comm();
-  GSICP_CUDA(cudaGetDevice(&c->device));
+  auto fail = [&](int code, const char* what, cudaError_t e) {
+    set_error("gsicp_comm_alloc: %s failed: %s", what, cudaGetErrorString(e));
+    if (c->h_status) cudaFreeHost(c->h_status);
+    if (c->local) cudaFree(c->local);
+    delete c;
+    return code;
+  };
+  cudaError_t e = cudaGetDevice(&c->device);
+  if (e != cudaSuccess) return fail(GSICP_ECUDA, "cudaGetDevice", e);
   c->bytes = kCommHeapOff + ((heap_bytes + 255) & ~size_t(255));
-  if (cudaMalloc((void**)&c->local, c->bytes) != cudaSuccess) {
-    set_error("gsicp_comm_alloc: cudaMalloc(%zu) failed: %s", c->bytes, cudaGetErrorString(cudaGetLastError()));
-    delete c;
-    return GSICP_ENOMEM;
-  }
-  GSICP_CUDA(cudaMemset(c->local, 0, c->bytes));
+  if ((e = cudaMalloc((void**)&c->local, c->bytes)) != cudaSuccess) return fail(GSICP_ENOMEM, "cudaMalloc", e);
+  if ((e = cudaMemset(c->local, 0, c->bytes)) != cudaSuccess) return fail(GSICP_ECUDA, "cudaMemset", e);
+  if ((e = cudaHostAlloc((void**)&c->h_status, 64, cudaHostAllocMapped)) != cudaSuccess) return fail(GSICP_ENOMEM, "cudaHostAlloc", e);
+  *c->h_status = 0;
+  if ((e = cudaHostGetDevicePointer((void**)&c->d_status, c->h_status, 0)) != cudaSuccess) return fail(GSICP_ECUDA, "cudaHostGetDevicePointer", e);
   cudaIpcMemHandle_t h;
-  const cudaError_t e = cudaIpcGetMemHandle(&h, c->local);
-  if (e != cudaSuccess) {
-    set_error("gsicp_comm_alloc: cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e));
-    cudaFree(c->local);
-    delete c;
-    return GSICP_ECUDA;
-  }
+  if ((e = cudaIpcGetMemHandle(&h, c->local)) != cudaSuccess) return fail(GSICP_ECUDA, "cudaIpcGetMemHandle", e);
   std::memcpy(handle64, &h, 64);
   *out = c;
   return GSICP_OK;
@@ -117,6 +123,7 @@ extern "C" void gsicp_comm_destroy(gsicp_comm* c) {
   for (int r = 0; r < c->world; r++)
     if (!c->local_only && r != c->rank && c->peer[r]) cudaIpcCloseMemHandle(c->peer[r]);
   if (c->local) cudaFree(c->local);
+  if (c->h_status) cudaFreeHost(c->h_status);
   delete c;
 }
 
