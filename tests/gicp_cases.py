@@ -101,3 +101,33 @@ def compare(a, b, exact_prefixes=("corr", "sqd", "tgt_rots", "src_rots", "tgt_sc
             assert np.array_equal(x, y), (k, int((x != y).sum()), x.size)
         else:
             raise AssertionError(f"unclassified key {k}")
+
+
+def unused_bindings(make, n_t=4000, n_s=3000, k=20, max_knn=99999.0):
+    """The FastGICP bindings the SLAM scripts never call (FG/src/python/main.cpp:169,172,203,205,228,246-253): z values +
+    calculate_target_covariance_withz, set_correspondence_randomness, a finite set_max_knn_distance, get_fitness_score,
+    swap_source_and_target."""
+    tgt, src, T = S.gicp_pair(n_t, n_s, 40, 41)
+    z = np.random.default_rng(5).uniform(0.2, 3.0, size=len(tgt)).astype(np.float32)
+    r = _params(make(), 0.05)
+    r.set_correspondence_randomness(k)
+    r.set_max_knn_distance(max_knn)
+    r.set_input_target(tgt)
+    r.set_target_z_values(z)
+    r.calculate_target_covariance_withz()
+    out = dict(tgt_rots=np.array(r.get_target_rotationsq()), tgt_scales_z=np.array(r.get_target_scales()))
+    r.set_input_source(src)
+    r.set_source_filter(len(src), _filter_all(len(src)))
+    out["pose"] = np.array(r.align(np.eye(4, dtype=np.float32)))
+    c, d = r.get_source_correspondence()
+    out.update(corr=np.array(c), sqd=np.array(d), src_rots=np.array(r.get_source_rotationsq()), src_scales=np.array(r.get_source_scales()),
+               H=np.array(r.get_final_hessian()))
+    out["fitness"] = np.array([r.get_fitness_score(x) for x in (1e-4, 0.01, 1e9)])
+    r.swap_source_and_target()
+    # after the swap the former target (with its withz covariances) is the source: the filter must cover it
+    r.set_source_filter(len(tgt), _filter_all(len(tgt)))
+    r.set_target_filter(len(src), _filter_all(len(src)))
+    out["pose_swapped"] = np.array(r.align(np.eye(4, dtype=np.float32)))
+    c, d = r.get_source_correspondence()
+    out.update(corr_swapped=np.array(c), sqd_swapped=np.array(d))
+    return out

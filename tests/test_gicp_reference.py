@@ -79,6 +79,21 @@ def test_oracle_matches_fast_gicp_golden():
 
 
 @needs_ref
+@pytest.mark.parametrize("kw", [dict(), dict(k=10), dict(max_knn=0.05)], ids=["k20", "k10", "knn-radius-0.05"])
+def test_oracle_matches_fast_gicp_on_the_bindings_the_slam_never_calls(kw):
+    """withz covariances + z values, set_correspondence_randomness, a finite k-NN radius, get_fitness_score and
+    swap_source_and_target (main.cpp:169,172,203,205,228,246-253): the oracle the CUDA path is tested against
+    (tests/test_gicp_gpu.py::test_unused_by_slam_bindings_match_oracle) is itself pinned to the real fast_gicp here."""
+    a, b = cases.unused_bindings(ref_gicp.FastGICP, **kw), cases.unused_bindings(_oracle, **kw)
+    for k in ("tgt_rots", "tgt_scales_z", "src_rots", "src_scales", "corr", "sqd", "corr_swapped", "sqd_swapped"):
+        assert np.array_equal(a[k], b[k]), k
+    assert np.array_equal(a["pose"], b["pose"]) and np.array_equal(a["pose_swapped"], b["pose_swapped"])
+    assert np.abs(a["H"] - b["H"]).max() <= 1e-12 * np.abs(a["H"]).max()
+    # getFitnessScore lives in PCL's Registration base class (here: oracle/pcl_shim): float transform of the cloud, 1-NN
+    assert np.allclose(a["fitness"], b["fitness"], rtol=2e-6, atol=0)
+
+
+@needs_ref
 def test_reference_module_is_the_reference():
     """The loaded module is the pybind11 module of main.cpp (its class list), not this repo's drop-in."""
     m = ref_gicp.load()
