@@ -131,3 +131,25 @@ def unused_bindings(make, n_t=4000, n_s=3000, k=20, max_knn=99999.0):
     c, d = r.get_source_correspondence()
     out.update(corr_swapped=np.array(c), sqd_swapped=np.array(d))
     return out
+
+
+def duplicates_and_outliers(make):
+    """Duplicated target points (k-NN / 1-NN ties resolved by the lowest index) and 50 source points 40 m outside the target
+    (no correspondence within max_corr: -1 rows), through the tracker's call sequence."""
+    tgt = S.sample_surface(3000, 30, 0.001)[0]
+    tgt[5] = tgt[6]
+    tgt[100] = tgt[2000]
+    src = S.sample_surface(500, 31, 0.001)[0]
+    src[:50] += 40.0
+    src[60] = src[61]
+    r = _params(make(), 0.1)
+    r.set_input_target(tgt)
+    r.set_target_filter(len(tgt), _filter_all(len(tgt)))
+    r.calculate_target_covariance_with_filter()
+    r.set_input_source(src)
+    r.set_source_filter(len(src), _filter_all(len(src)))
+    out = dict(pose=np.array(r.align(np.eye(4, dtype=np.float32))))
+    c, d = r.get_source_correspondence()
+    out.update(corr=np.array(c), sqd=np.array(d), tgt_rots=np.array(r.get_target_rotationsq()), tgt_scales=np.array(r.get_target_scales()),
+               src_rots=np.array(r.get_source_rotationsq()), src_scales=np.array(r.get_source_scales()), H=np.array(r.get_final_hessian()))
+    return out

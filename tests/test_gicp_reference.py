@@ -94,6 +94,14 @@ def test_oracle_matches_fast_gicp_on_the_bindings_the_slam_never_calls(kw):
 
 
 @needs_ref
+def test_oracle_matches_fast_gicp_with_duplicates_and_outliers():
+    """Ties (duplicated points in both clouds) and source points with no correspondence within max_corr (-1 rows)."""
+    a, b = cases.duplicates_and_outliers(ref_gicp.FastGICP), cases.duplicates_and_outliers(_oracle)
+    cases.compare(a, b)
+    assert (a["corr"][:50] == -1).all() and np.array_equal(a["pose"], b["pose"])
+
+
+@needs_ref
 def test_reference_module_is_the_reference():
     """The loaded module is the pybind11 module of main.cpp (its class list), not this repo's drop-in."""
     m = ref_gicp.load()
