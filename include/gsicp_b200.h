@@ -231,9 +231,13 @@ int gsicp_gicp_set_shard(gsicp_gicp*, int shard_count, int shard_index,
  * the peers' segments and polling sequence flags: no host hop and no second kernel per exchange.
  *   GICP:        source points (LM linearisation AND k-NN covariances) are sharded over the ranks; the 28-double normal
  *                equations / the 1-double error are exchanged inside the persistent LM kernel (fgi:296-378).
- *   rasterizer:  screen tiles are sharded; the per-Gaussian render moments accumulate in the segment and every rank adds
- *                the world's rows of the visible Gaussians in rank order inside gsicp_raster_backward.
- * heap_bytes: per-rank exchange heap (>= 96 bytes per Gaussian for the rasterizer; merges of sharded getters use its upper half). */
+ *   rasterizer:  screen tiles are sharded; the per-Gaussian render moments accumulate in the segment and are all-reduced
+ *                inside gsicp_raster_backward as a reduce-scatter + all-gather of P2P loads (rank r sums the world's rows of
+ *                its slice of the table in rank order, every rank then copies each row from its owner).
+ * heap_bytes: per-rank exchange heap (>= 96 bytes per Gaussian for the rasterizer: accumulators in the lower half, the reduced
+ * slice / the staging of sharded getters in the upper half).  Every rank must issue the same exchanging calls in the same
+ * order.  A barrier whose peer never arrives gives up after its poll budget; the next exchanging call then returns GSICP_ECUDA
+ * ("a peer did not arrive") instead of continuing with partial sums. */
 typedef struct gsicp_comm gsicp_comm;
 int gsicp_comm_alloc(size_t heap_bytes, gsicp_comm** out, void* handle64);
 int gsicp_comm_connect(gsicp_comm*, int world, int rank, const void* handles /* world x 64 bytes, rank order */);
