@@ -1,10 +1,12 @@
 """Multi-GPU host logic: one process per GPU, torch.distributed (NCCL on the GPUs, gloo in the CPU tests).
 
 * rasterizer: screen tiles are interleaved over the ranks (tile % world == rank).  Every rank preprocesses all Gaussians
-  but emits / sorts / renders only its own tiles; the loss is evaluated on the rank's own pixels with the GLOBAL
-  normalisation, so the per-Gaussian parameter gradients of the ranks simply add: one all-reduce per iteration.
-* GICP: source points are split into contiguous ranges; the 28 doubles of the normal equations (21 H + 6 b + error)
-  are all-reduced before the (replicated) host LM step reads them.
+  but emits / sorts / renders only its own tiles and feeds the image gradients of its own pixels; the per-Gaussian render
+  moments of the ranks add up inside gsicp_raster_backward, so every rank ends with the complete parameter gradients.
+* GICP: source points are split into contiguous ranges (k-NN covariances and the LM loop); the 28 doubles of the normal
+  equations (21 H + 6 b + error) are exchanged at every reduction point.
+`ShardGroup` wires both to the library's in-kernel exchange over peer memory (csrc/comm.cuh) and falls back to
+torch.distributed collectives reached through the library's callbacks; the helpers above it serve the fallback and the tests.
 """
 import torch
 
@@ -119,24 +121,28 @@ class ShardGroup:
 
         import torch.distributed as dist
 
-        from ._lib import check, lib
+        from ._lib import last_error, lib
 
         comm = C.c_void_p()
         handle = C.create_string_buffer(64)
+
         with torch.cuda.device(self.device):
-            check(lib.gsicp_comm_alloc(int(heap_bytes), C.byref(comm), handle), "gsicp_comm_alloc")
+            # a rank whose allocation fails still takes part in the two collectives below, so nobody is left waiting
+            alloc_rc = lib.gsicp_comm_alloc(int(heap_bytes), C.byref(comm), handle)
+            why = last_error() if alloc_rc != 0 else ""
             handles = [None] * self.world
-            dist.all_gather_object(handles, bytes(handle.raw), group=self.group)
+            dist.all_gather_object(handles, bytes(handle.raw) if alloc_rc == 0 else None, group=self.group)
             ok = all(isinstance(h, (bytes, bytearray)) and len(h) == 64 for h in handles)
             rc = lib.gsicp_comm_connect(comm, self.world, self.rank, b"".join(handles)) if ok else -1
+            if ok and rc != 0:
+                why = last_error()
             # every rank must agree before anybody relies on the peers' segments
             flag = torch.tensor([1 if rc == 0 else 0], device=self.device)
             dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
             if int(flag.item()) != 1:
-                lib.gsicp_comm_destroy(comm)
-                from ._lib import last_error
-
-                raise RuntimeError("gsicp_comm_connect failed on some rank: " + (last_error() if rc != 0 else "peer"))
+                if alloc_rc == 0:
+                    lib.gsicp_comm_destroy(comm)
+                raise RuntimeError("exchange group could not be set up on every rank: " + (why or "a peer failed"))
         self._comm = comm
 
     def _allreduce(self, typestr):
